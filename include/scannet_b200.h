@@ -1,0 +1,214 @@
+/* scannet_b200 — C ABI of the B200-native ScanNet hot path.
+ *
+ * The reference toolkit exposes NO plugin / operator / FFI interface: its
+ * seams are three command-line tools and two C++ function/class seams.  Each entry point
+ * below names the reference interface it stands in for (paths relative to /root/reference).
+ *
+ * Conventions: plain C, opaque handles, int status (0 = ok, <0 = error; text via
+ * scn_last_error(), thread-local), caller-owned output buffers unless stated, no
+ * exceptions cross the boundary, one CUDA stream per handle, handles are not thread-safe.
+ * Every compute entry point runs on the GPU; there is no CPU fallback — without a usable
+ * CUDA device the call fails with SCN_ERR_CUDA.
+ */
+#ifndef SCANNET_B200_H
+#define SCANNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCN_OK              0
+#define SCN_ERR_ARG        -1   /* bad argument */
+#define SCN_ERR_CUDA       -2   /* CUDA runtime / no device */
+#define SCN_ERR_IO         -3   /* file could not be opened / read / written */
+#define SCN_ERR_FORMAT     -4   /* malformed .sens / .ply / .obj / parameter file */
+#define SCN_ERR_CAPACITY   -5   /* hash table or block heap exhausted */
+#define SCN_ERR_UNSUPPORTED -6  /* e.g. TYPE_OCCI_USHORT depth (needs uplink codec, sensorData.h:711-722) */
+
+const char* scn_last_error(void);
+int  scn_version(void);
+/* Number of CUDA devices visible (<0 on error). */
+int  scn_device_count(void);
+/* Pinned host memory for frame staging (cudaHostAlloc); integrate calls detect it and skip the bounce copy. */
+void* scn_host_alloc(size_t bytes);
+void  scn_host_free(void* p);
+void  scn_free(void* p);                      /* frees buffers this library malloc'ed for the caller */
+
+/* ===================================================================== Segmentator ====
+ * Replaces: std::vector<int> segment(const std::string&, float, int)   Segmentator/segmentator.cpp:123
+ *           universe* segment_graph(int, int, edge*, float)            Segmentator/segmentator.cpp:71
+ *           main / writeToJSON                                         Segmentator/segmentator.cpp:253-288
+ */
+
+/* Mesh loading with the same acceptance rules as the reference loader (tinyply path
+ * segmentator.cpp:130-140: vertex x,y,z must be 4-byte floats, face list property
+ * "vertex_indices" or "vertex_index" with 4-byte indices, triangles only; OBJ path :141-172:
+ * original vertices, first shape only).  Buffers are malloc'ed; release with scn_free. */
+int scn_mesh_load(const char* path, float** xyz, uint64_t* n_verts, uint32_t** tri, uint64_t* n_faces);
+
+/* flags for scn_segment_mesh */
+#define SCN_SEG_DEFAULT        0
+#define SCN_SEG_HOST_UNIONFIND 1   /* run the Kruskal / small-segment replay on the host instead of the GPU kernel */
+
+/* segment() over raw arrays: seg_out[v] = root vertex id of v's segment, bit-identical to the
+ * reference compiled with libstdc++ (incl. std::sort's unstable tie order). */
+int scn_segment_mesh(const float* xyz, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces,
+                     float k_thresh, int32_t seg_min_verts, int32_t* seg_out, int flags);
+
+/* Intermediates for parity tests: 12-byte {float w; int32 a; int32 b} records, 3 per face,
+ * before and after the sort (either pointer may be NULL). */
+int scn_segment_mesh_debug(const float* xyz, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces,
+                           float k_thresh, int32_t seg_min_verts, int32_t* seg_out, int flags,
+                           void* edges_presort, void* edges_sorted, float* vertex_normals,
+                           int32_t* roots_after_kruskal);
+
+/* segment_graph(): sorts `edges` (12-byte records) in place exactly like the reference and
+ * returns find(v) / size(find(v)) for every vertex after the thresholded Kruskal pass. */
+int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c,
+                      int32_t* roots_out, int32_t* sizes_out, int flags);
+
+/* writeToJSON(): one-line JSON, same byte layout as segmentator.cpp:253-266. */
+int scn_write_segs_json(const char* path, const char* scene_id, float k_thresh, int32_t seg_min_verts,
+                        const int32_t* seg_indices, uint64_t n);
+
+/* The CLI in library form: `segmentator input.ply [kThresh] [segMinVerts]` (same stdout
+ * lines, same output file name <base>.<%f kThresh>.segs.json). Returns the process exit code. */
+int scn_segmentator_main(int argc, const char** argv);
+
+/* per-stage timings of the last scn_segment_* call on this thread, milliseconds:
+ * [0] H2D, [1] normals, [2] weights, [3] sort, [4] kruskal, [5] small-merge, [6] labels+D2H, [7] total */
+int scn_segment_last_timings(float* ms8);
+
+/* ===================================================================== SensReader =====
+ * Replaces: ml::SensorData                                  SensReader/c++/src/sensorData.h:285-1936
+ *   ctor/loadFromFile :855,:1250   decompressDepthAlloc :939-946   decompressColorAlloc :929-936
+ *   saveToFile :1101-1109          saveToImages :1380-1466         operator<< :1941-1955
+ */
+typedef struct scn_sens scn_sens;
+
+typedef struct {
+  uint32_t version;                 /* 4 */
+  uint32_t color_width, color_height, depth_width, depth_height;
+  int32_t  color_compression;       /* -1 unknown, 0 raw, 1 png, 2 jpeg   (sensorData.h:346-351) */
+  int32_t  depth_compression;       /* -1 unknown, 0 raw u16, 1 zlib u16, 2 occi u16 (:352-357) */
+  float    depth_shift;
+  uint64_t n_frames, n_imu_frames;
+  float    color_intrinsic[16], color_extrinsic[16], depth_intrinsic[16], depth_extrinsic[16];
+  char     sensor_name[256];
+} scn_sens_info_t;
+
+int  scn_sens_open(const char* path, scn_sens** out);
+void scn_sens_close(scn_sens* s);
+int  scn_sens_info(const scn_sens* s, scn_sens_info_t* info);
+/* camera-to-world (row-major 4x4; all -inf = invalid) + timestamps + compressed sizes */
+int  scn_sens_frame_meta(const scn_sens* s, uint64_t frame, float cam2world[16], uint64_t* ts_color,
+                         uint64_t* ts_depth, uint64_t* color_bytes, uint64_t* depth_bytes);
+/* decoded depth, depth_width*depth_height uint16 (0 = invalid), caller-owned buffer */
+int  scn_sens_frame_depth_u16(const scn_sens* s, uint64_t frame, uint16_t* out);
+/* decoded colour, color_width*color_height*3 RGB8, caller-owned buffer */
+int  scn_sens_frame_color_rgb8(const scn_sens* s, uint64_t frame, uint8_t* out);
+/* raw compressed payloads (pointers into the handle; valid until scn_sens_close) */
+int  scn_sens_frame_payload(const scn_sens* s, uint64_t frame, const uint8_t** color, const uint8_t** depth);
+/* replace a frame's pose (as `recons` writes optimised trajectories back, zParametersScanNet.txt:5) */
+int  scn_sens_set_pose(scn_sens* s, uint64_t frame, const float cam2world[16]);
+int  scn_sens_save(const scn_sens* s, const char* path);
+/* saveToImages(): _info.txt, frame-%06d.color.{jpg,png}, .depth.pgm (P5, 16-bit BE), .pose.txt */
+int  scn_sens_save_to_images(const scn_sens* s, const char* out_dir);
+/* operator<< text (header summary) into a caller buffer; returns needed length */
+int64_t scn_sens_describe(const scn_sens* s, char* buf, uint64_t cap);
+
+/* Writer (initDefault + addFrame + saveToFile pattern, sensorData.h:888-929; Converter/main.cpp:32-41) */
+int  scn_sens_create(uint32_t color_w, uint32_t color_h, uint32_t depth_w, uint32_t depth_h,
+                     const float color_intrinsic[16], const float depth_intrinsic[16],
+                     int32_t color_compression, int32_t depth_compression, float depth_shift,
+                     const char* sensor_name, scn_sens** out);
+/* colour: raw RGB8 (color_compression 0) or an already-encoded JPEG/PNG payload of color_bytes bytes */
+int  scn_sens_add_frame(scn_sens* s, const uint8_t* color, uint64_t color_bytes, const uint16_t* depth,
+                        const float cam2world[16], uint64_t ts_color, uint64_t ts_depth);
+/* The CLI in library form: `sens <file.sens> [outDir=./out/]` (SensReader/c++/src/main.cpp:28-97). */
+int  scn_sens_main(int argc, const char** argv);
+
+/* ===================================================================== TSDF fusion =====
+ * Replaces: the external FriedLiver.exe / DepthSensing.exe stage
+ *   Server/scan_processor.py:27-35,123-138   (`<exe> <params.txt> <params2.txt> <file.sens>` -> .ply)
+ * whose source is NOT in the reference tree.  Numerical spec: DESIGN.md "TSDF spec v1".
+ */
+typedef struct scn_tsdf scn_tsdf;
+
+typedef struct {
+  float    voxel_size;                /* s_SDFVoxelSize               (BASELINE.json: 0.004)           */
+  float    trunc_base;                /* s_SDFTruncation                                                */
+  float    trunc_scale;               /* s_SDFTruncationScale (m per m of depth)                        */
+  float    depth_min, depth_max;      /* s_sensorDepthMin/Max         zParametersScanNet.txt:34-35      */
+  float    max_integration_distance;  /* s_SDFMaxIntegrationDistance  :51                               */
+  uint32_t weight_sample;             /* s_SDFIntegrationWeightSample :52                               */
+  uint32_t weight_max;                /* s_SDFIntegrationWeightMax    :53 (clamped to 255: u8 weight)   */
+  uint32_t width, height;             /* integration resolution (BASELINE.json: 640x480)                */
+  float    depth_shift;               /* .sens header depthShift (1000)                                 */
+  uint64_t hash_slots;                /* open-addressing slots (rounded up to a power of two)           */
+  uint64_t max_blocks;                /* 8^3 voxel blocks in the heap (4 KiB each)  s_hashNumSDFBlocks  */
+  uint32_t batch_frames;              /* frames fused per block residency, 1..32                        */
+  uint32_t flags;                     /* SCN_TSDF_* */
+} scn_tsdf_params;
+
+#define SCN_TSDF_NO_STATS   1u        /* skip the per-launch counters (N_u, N_b) */
+#define SCN_TSDF_KERNEL_SIMPLE 2u     /* use the plain (non TMA-staged) integrate kernel */
+
+typedef struct {
+  uint64_t frames_integrated, frames_skipped;   /* skipped = invalid (-inf) pose */
+  uint64_t blocks_allocated;                    /* live blocks in the heap */
+  uint64_t voxels_updated;                      /* Σ_frames N_u */
+  uint64_t blocks_visited;                      /* Σ_frames N_b */
+  uint64_t algorithmic_bytes;                   /* Σ_frames 2WH + 3WH[colour] + 16 N_u + 16 N_b */
+  uint64_t kernel_launches;                     /* kernels this handle launched so far */
+  uint32_t error_flags;                         /* bit0 heap full, bit1 table full */
+} scn_tsdf_stats_t;
+
+void scn_tsdf_default_params(scn_tsdf_params* p);
+/* `key = value;` parameter files as consumed by the external binaries (Server/tools/recons/zParameters*.txt);
+ * unknown keys are ignored, known ones override *p. */
+int  scn_tsdf_params_from_file(const char* path, scn_tsdf_params* p);
+int  scn_tsdf_create(const scn_tsdf_params* p, int device, scn_tsdf** out);
+void scn_tsdf_destroy(scn_tsdf* t);
+/* Use an existing CUDA stream (cudaStream_t cast to void*; NULL = legacy default stream). */
+int  scn_tsdf_set_stream(scn_tsdf* t, void* cuda_stream);
+/* One frame from HOST buffers: depth W*H u16, rgb W*H*3 (nullable; must already be registered to
+ * the depth image), cam2world row-major 4x4, K = 4x4 depth intrinsic as in the .sens header.
+ * Frames whose pose is invalid (cam2world[0] == -inf) are skipped. Asynchronous. */
+int  scn_tsdf_integrate(scn_tsdf* t, const uint16_t* depth, const uint8_t* rgb,
+                        const float cam2world[16], const float K[16]);
+/* n frames from HOST buffers (contiguous frames; poses n*16); H2D copies are pipelined against the
+ * kernels.  Identical results to n calls of scn_tsdf_integrate. */
+int  scn_tsdf_integrate_batch(scn_tsdf* t, uint32_t n, const uint16_t* depth, const uint8_t* rgb,
+                              const float* cam2world, const float K[16]);
+/* n frames whose depth/rgb already live in DEVICE memory (poses stay on the host). */
+int  scn_tsdf_integrate_device(scn_tsdf* t, uint32_t n, const uint16_t* d_depth, const uint8_t* d_rgb,
+                               const float* cam2world, const float K[16]);
+int  scn_tsdf_sync(scn_tsdf* t);
+int  scn_tsdf_reset(scn_tsdf* t);
+int  scn_tsdf_stats(scn_tsdf* t, scn_tsdf_stats_t* out);
+/* Optional per-kernel timing: when enabled, CUDA events are recorded on the handle's stream around the
+ * alloc and integrate kernels of every batch; scn_tsdf_kernel_times sums them (ms) since enabling.
+ * union_blocks = Σ_launches blocks read+written by the integrate kernel (actual 8 KiB/block traffic). */
+int  scn_tsdf_profile(scn_tsdf* t, int enable);
+int  scn_tsdf_kernel_times(scn_tsdf* t, double* alloc_ms, double* integrate_ms, uint64_t* n_batches,
+                           uint64_t* union_blocks);
+/* Copies up to `cap` blocks to the host: block_xyz 3*n int32 block coordinates, voxels n*512
+ * records of {float sdf; uint8 r,g,b,weight}, x fastest.  Order is heap order (unspecified). */
+int  scn_tsdf_download_blocks(scn_tsdf* t, int32_t* block_xyz, void* voxels, uint64_t cap, uint64_t* n);
+/* Marching-cubes surface of the current volume (malloc'ed; scn_free).  rgb may be NULL. */
+int  scn_tsdf_extract_mesh(scn_tsdf* t, float** xyz, uint8_t** rgb, uint32_t** tri,
+                           uint64_t* n_verts, uint64_t* n_faces);
+/* PLY writer in the VCGLIB layout Segmentator reads (Server/config/scan_stages.json:33-37). */
+int  scn_mesh_save_ply(const char* path, const float* xyz, const uint8_t* rgb, uint64_t n_verts,
+                       const uint32_t* tri, uint64_t n_faces);
+/* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract. */
+int  scn_fuse_main(int argc, const char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANNET_B200_H */

@@ -1,0 +1,285 @@
+/* TEST INFRASTRUCTURE — scalar CPU statement of the TSDF voxel-block integration.
+ *
+ * PARITY UNPINNED.  The reference tree contains NO TSDF source: reconstruction is done
+ * by the external FriedLiver.exe (BundleFusion) / DepthSensing.exe (VoxelHashing)
+ * binaries (/root/reference/Server/scan_processor.py:27-35,126,138), neither vendored
+ * nor version-pinned.  No golden vector, test or fixture in
+ * the reference constrains any TSDF value.  This file is therefore the single source of
+ * truth for the numerical spec written down in DESIGN.md §"TSDF spec v1"; the CUDA path
+ * is compared against it (bit-exact where stated, since the spec is written in terms of
+ * correctly-rounded IEEE binary32 operations and explicit fmaf()).
+ *
+ * In-tree statements this spec follows:
+ *   parameters            Server/tools/recons/zParametersScanNet.txt:34-35,47-58
+ *   back-projection       SensReader/c++/src/sensorData.h:1577-1578, filter.cu:87
+ *   depth units / invalid sensorData.h:972-974 (value / depthShift, 0 = invalid)
+ *   invalid pose          sensorData.h:382 (all -inf)
+ *   block hash primes     external/mLib/include/core-util/sparseGrid3.h:14-17 (GPU side only)
+ * Everything else (8^3 blocks, voxel {f32 sdf, rgb8, u8 weight}, ray-band allocation,
+ * weighted running average) is the published VoxelHashing scheme (Niessner et al. 2013),
+ * restated from the paper's description, not from source.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  Compile: -O2 -ffp-contract=off -mfma (fmaf must be fused).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+  float voxel_size, trunc_base, trunc_scale, depth_min, depth_max, max_integration_distance;
+  uint32_t weight_sample, weight_max;
+  uint32_t width, height;
+  float depth_shift;
+} oracle_tsdf_params;
+
+typedef struct { float sdf; uint8_t r, g, b, w; } ovoxel;        /* 8 bytes */
+
+typedef struct {
+  oracle_tsdf_params p;
+  /* open-addressing table: key -> block index */
+  uint64_t cap; uint64_t* keys; int32_t* vals;
+  /* block store */
+  uint64_t n_blocks, blocks_cap; uint64_t* block_key; ovoxel* vox; uint32_t* touched_stamp;
+  /* per-frame scratch */
+  int32_t* touched; uint64_t n_touched, touched_cap; float* dm;
+  uint32_t frame_no;
+  /* counters */
+  uint64_t last_updated, last_touched, total_updated, total_touched, frames_done, frames_skipped;
+  int threads;
+} oracle_tsdf;
+
+#define EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define KEY_BIAS  (1 << 20)
+
+static inline int key_ok(int x, int y, int z) {
+  return x >= -KEY_BIAS && x < KEY_BIAS && y >= -KEY_BIAS && y < KEY_BIAS && z >= -KEY_BIAS && z < KEY_BIAS;
+}
+static inline uint64_t pack_key(int x, int y, int z) {
+  return (uint64_t)(uint32_t)(x + KEY_BIAS) | ((uint64_t)(uint32_t)(y + KEY_BIAS) << 21) |
+         ((uint64_t)(uint32_t)(z + KEY_BIAS) << 42);
+}
+static inline void unpack_key(uint64_t k, int32_t* xyz) {
+  xyz[0] = (int32_t)(k & 0x1FFFFF) - KEY_BIAS;
+  xyz[1] = (int32_t)((k >> 21) & 0x1FFFFF) - KEY_BIAS;
+  xyz[2] = (int32_t)((k >> 42) & 0x1FFFFF) - KEY_BIAS;
+}
+static inline uint64_t mix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33; return k;
+}
+
+static void table_grow(oracle_tsdf* o) {
+  uint64_t ncap = o->cap * 2;
+  uint64_t* nk = (uint64_t*)malloc(ncap * 8); int32_t* nv = (int32_t*)malloc(ncap * 4);
+  for (uint64_t i = 0; i < ncap; ++i) nk[i] = EMPTY_KEY;
+  for (uint64_t i = 0; i < o->cap; ++i) if (o->keys[i] != EMPTY_KEY) {
+    uint64_t s = mix64(o->keys[i]) & (ncap - 1);
+    while (nk[s] != EMPTY_KEY) s = (s + 1) & (ncap - 1);
+    nk[s] = o->keys[i]; nv[s] = o->vals[i];
+  }
+  free(o->keys); free(o->vals); o->keys = nk; o->vals = nv; o->cap = ncap;
+}
+
+/* find-or-create; marks the block touched for the current frame */
+static void touch_block(oracle_tsdf* o, int bx, int by, int bz) {
+  if (!key_ok(bx, by, bz)) return;
+  const uint64_t key = pack_key(bx, by, bz);
+  uint64_t s = mix64(key) & (o->cap - 1);
+  while (o->keys[s] != EMPTY_KEY && o->keys[s] != key) s = (s + 1) & (o->cap - 1);
+  int32_t idx;
+  if (o->keys[s] == key) idx = o->vals[s];
+  else {
+    if (o->n_blocks == o->blocks_cap) {
+      o->blocks_cap *= 2;
+      o->block_key = (uint64_t*)realloc(o->block_key, o->blocks_cap * 8);
+      o->vox = (ovoxel*)realloc(o->vox, o->blocks_cap * 512 * sizeof(ovoxel));
+      o->touched_stamp = (uint32_t*)realloc(o->touched_stamp, o->blocks_cap * 4);
+    }
+    idx = (int32_t)o->n_blocks++;
+    o->block_key[idx] = key;
+    memset(o->vox + (size_t)idx * 512, 0, 512 * sizeof(ovoxel));
+    o->touched_stamp[idx] = 0;
+    o->keys[s] = key; o->vals[s] = idx;
+    if (o->n_blocks * 2 > o->cap) table_grow(o);
+  }
+  if (o->touched_stamp[idx] != o->frame_no) {
+    o->touched_stamp[idx] = o->frame_no;
+    if (o->n_touched == o->touched_cap) {
+      o->touched_cap *= 2; o->touched = (int32_t*)realloc(o->touched, o->touched_cap * 4);
+    }
+    o->touched[o->n_touched++] = idx;
+  }
+}
+
+oracle_tsdf* oracle_tsdf_create(const oracle_tsdf_params* p, int threads) {
+  oracle_tsdf* o = (oracle_tsdf*)calloc(1, sizeof(oracle_tsdf));
+  o->p = *p;
+  if (o->p.weight_max > 255) o->p.weight_max = 255;
+  o->cap = 1 << 16; o->keys = (uint64_t*)malloc(o->cap * 8); o->vals = (int32_t*)malloc(o->cap * 4);
+  for (uint64_t i = 0; i < o->cap; ++i) o->keys[i] = EMPTY_KEY;
+  o->blocks_cap = 1 << 12;
+  o->block_key = (uint64_t*)malloc(o->blocks_cap * 8);
+  o->vox = (ovoxel*)malloc(o->blocks_cap * 512 * sizeof(ovoxel));
+  o->touched_stamp = (uint32_t*)malloc(o->blocks_cap * 4);
+  o->touched_cap = 1 << 12; o->touched = (int32_t*)malloc(o->touched_cap * 4);
+  o->dm = (float*)malloc((size_t)p->width * p->height * 4);
+  o->threads = threads > 0 ? threads : 1;
+  return o;
+}
+void oracle_tsdf_destroy(oracle_tsdf* o) {
+  if (!o) return;
+  free(o->keys); free(o->vals); free(o->block_key); free(o->vox); free(o->touched_stamp);
+  free(o->touched); free(o->dm); free(o);
+}
+
+/* ---- spec step B: ray-band block allocation for one pixel ---------------------------- */
+static void alloc_pixel(oracle_tsdf* o, const float* T, float fx, float fy, float cx, float cy,
+                        float inv_bs, int x, int y, float d) {
+  const oracle_tsdf_params* p = &o->p;
+  if (!(d >= p->depth_min && d <= p->depth_max)) return;
+  if (d >= p->max_integration_distance) return;
+  const float tr = fmaf(p->trunc_scale, d, p->trunc_base);
+  const float zmin = fminf(p->max_integration_distance, d - tr);
+  const float zmax = fminf(p->max_integration_distance, d + tr);
+  if (zmin >= zmax) return;
+  const float rx = ((float)x - cx) / fx, ry = ((float)y - cy) / fy;
+  float A[3], Bp[3];
+  for (int e = 0; e < 2; ++e) {
+    const float Z = e ? zmax : zmin, X = rx * Z, Y = ry * Z;
+    float* dst = e ? Bp : A;
+    for (int i = 0; i < 3; ++i) {
+      const float w = fmaf(T[4 * i + 2], Z, fmaf(T[4 * i + 1], Y, fmaf(T[4 * i + 0], X, T[4 * i + 3])));
+      dst[i] = fmaf(w, inv_bs, 0.0625f);
+    }
+  }
+  int cell[3], end[3], step[3]; float tmax[3], tdelta[3];
+  for (int i = 0; i < 3; ++i) {
+    cell[i] = (int)floorf(A[i]); end[i] = (int)floorf(Bp[i]);
+    const float dir = Bp[i] - A[i];
+    if (dir > 0.0f)      { step[i] = 1;  tmax[i] = ((float)(cell[i] + 1) - A[i]) / dir; tdelta[i] = 1.0f / dir; }
+    else if (dir < 0.0f) { step[i] = -1; tmax[i] = ((float)cell[i] - A[i]) / dir;       tdelta[i] = -1.0f / dir; }
+    else                 { step[i] = 0;  tmax[i] = INFINITY; tdelta[i] = INFINITY; }
+  }
+  for (int it = 0; it < 48; ++it) {
+    touch_block(o, cell[0], cell[1], cell[2]);
+    if (cell[0] == end[0] && cell[1] == end[1] && cell[2] == end[2]) return;
+    int ax;
+    if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) ax = 0; else if (tmax[1] <= tmax[2]) ax = 1; else ax = 2;
+    if (tmax[ax] > 1.0f) break;
+    cell[ax] += step[ax];
+    tmax[ax] += tdelta[ax];
+  }
+  touch_block(o, end[0], end[1], end[2]);
+}
+
+/* ---- spec step C: integrate one block ------------------------------------------------ */
+static uint64_t integrate_block(oracle_tsdf* o, int32_t idx, const float* Rt, const float* tinv,
+                                const float* Avs, float fx, float fy, float cx, float cy,
+                                const uint8_t* rgb) {
+  const oracle_tsdf_params* p = &o->p;
+  const int W = (int)p->width, H = (int)p->height;
+  int32_t b[3]; unpack_key(o->block_key[idx], b);
+  float org[3], base[3];
+  for (int i = 0; i < 3; ++i) org[i] = (float)(8 * b[i]) * p->voxel_size;
+  for (int i = 0; i < 3; ++i)
+    base[i] = fmaf(Rt[3 * i + 2], org[2], fmaf(Rt[3 * i + 1], org[1], fmaf(Rt[3 * i + 0], org[0], tinv[i])));
+  const float inv_range = 1.0f / (p->depth_max - p->depth_min);
+  const float ws15 = (float)p->weight_sample * 1.5f;
+  ovoxel* vb = o->vox + (size_t)idx * 512;
+  uint64_t n_upd = 0;
+  for (int lz = 0; lz < 8; ++lz) for (int ly = 0; ly < 8; ++ly) for (int lx = 0; lx < 8; ++lx) {
+    float pc[3];
+    for (int i = 0; i < 3; ++i)
+      pc[i] = fmaf((float)lz, Avs[3 * i + 2], fmaf((float)ly, Avs[3 * i + 1], fmaf((float)lx, Avs[3 * i + 0], base[i])));
+    const float z = pc[2];
+    if (!(z > 0.0f)) continue;
+    const float rz = 1.0f / z;
+    const float u = fmaf(pc[0] * rz, fx, cx), v = fmaf(pc[1] * rz, fy, cy);
+    const long ix = lrintf(u), iy = lrintf(v);                 /* round-half-even */
+    if (ix < 0 || ix >= W || iy < 0 || iy >= H) continue;
+    const float d = o->dm[iy * W + ix];
+    if (!(d >= p->depth_min && d <= p->depth_max)) continue;
+    const float sdf = d - z;
+    const float tr = fmaf(p->trunc_scale, d, p->trunc_base);
+    if (!(sdf > -tr)) continue;
+    const float s = fminf(sdf, tr);
+    const float dz01 = (d - p->depth_min) * inv_range;
+    const float wf = fmaxf(ws15 * (1.0f - dz01), 1.0f);
+    const int w1 = (int)wf;
+    ovoxel* vx = vb + (lz * 64 + ly * 8 + lx);
+    const int w0 = vx->w, wsum = w0 + w1;
+    const float inv = 1.0f / (float)wsum, w0f = (float)w0, w1f = (float)w1;
+    vx->sdf = fmaf(vx->sdf, w0f, s * w1f) * inv;
+    if (rgb) {
+      const uint8_t* c1 = rgb + 3 * ((size_t)iy * W + ix);
+      vx->r = (uint8_t)(int)(fmaf((float)vx->r, w0f, (float)c1[0] * w1f) * inv + 0.5f);
+      vx->g = (uint8_t)(int)(fmaf((float)vx->g, w0f, (float)c1[1] * w1f) * inv + 0.5f);
+      vx->b = (uint8_t)(int)(fmaf((float)vx->b, w0f, (float)c1[2] * w1f) * inv + 0.5f);
+    }
+    vx->w = (uint8_t)(wsum < (int)p->weight_max ? wsum : (int)p->weight_max);
+    ++n_upd;
+  }
+  return n_upd;
+}
+
+/* One frame.  K is the 4x4 row-major depth intrinsic as stored in a .sens header
+ * (sensorData.h:300-307): fx=K[0], cx=K[2], fy=K[5], cy=K[6].  Returns 1 if the frame was
+ * skipped (invalid pose), 0 otherwise. */
+int oracle_tsdf_integrate(oracle_tsdf* o, const uint16_t* depth, const uint8_t* rgb,
+                          const float* T /*cam2world 16*/, const float* K /*16*/) {
+  const oracle_tsdf_params* p = &o->p;
+  const int W = (int)p->width, H = (int)p->height;
+  o->last_updated = o->last_touched = 0;
+  if (T[0] == -INFINITY) { o->frames_skipped++; return 1; }
+  const float fx = K[0], cx = K[2], fy = K[5], cy = K[6];
+  o->frame_no++;
+  o->n_touched = 0;
+  /* step A: depth in metres */
+  for (int i = 0; i < W * H; ++i) o->dm[i] = depth[i] == 0 ? 0.0f : (float)depth[i] / p->depth_shift;
+  /* per-frame constants */
+  float Rt[9], tinv[3], Avs[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt[3 * i + j] = T[4 * j + i];
+  for (int i = 0; i < 3; ++i)
+    tinv[i] = -((Rt[3 * i + 0] * T[3] + Rt[3 * i + 1] * T[7]) + Rt[3 * i + 2] * T[11]);
+  for (int i = 0; i < 9; ++i) Avs[i] = Rt[i] * p->voxel_size;
+  const float inv_bs = 1.0f / (8.0f * p->voxel_size);
+  /* step B (sequential: the touched SET does not depend on order) */
+  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+    alloc_pixel(o, T, fx, fy, cx, cy, inv_bs, x, y, o->dm[y * W + x]);
+  /* step C (blocks are independent) */
+  uint64_t n_upd = 0;
+  const int64_t nt = (int64_t)o->n_touched;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_upd) num_threads(o->threads)
+  for (int64_t t = 0; t < nt; ++t)
+    n_upd += integrate_block(o, o->touched[t], Rt, tinv, Avs, fx, fy, cx, cy, rgb);
+  o->last_updated = n_upd; o->last_touched = o->n_touched;
+  o->total_updated += n_upd; o->total_touched += o->n_touched; o->frames_done++;
+  return 0;
+}
+
+uint64_t oracle_tsdf_num_blocks(const oracle_tsdf* o) { return o->n_blocks; }
+void oracle_tsdf_counters(const oracle_tsdf* o, uint64_t* out /*6*/) {
+  out[0] = o->last_updated; out[1] = o->last_touched; out[2] = o->total_updated;
+  out[3] = o->total_touched; out[4] = o->frames_done; out[5] = o->frames_skipped;
+}
+
+static int cmp_u64idx(const void* a, const void* b) {
+  const uint64_t x = ((const uint64_t*)a)[0], y = ((const uint64_t*)b)[0];
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+/* Blocks sorted by packed key.  block_xyz: 3*n int32, voxels: n*512*8 bytes {f32 sdf, r,g,b,w}. */
+void oracle_tsdf_export(const oracle_tsdf* o, int32_t* block_xyz, void* voxels) {
+  const uint64_t n = o->n_blocks;
+  uint64_t* ki = (uint64_t*)malloc((n ? n : 1) * 16);
+  for (uint64_t i = 0; i < n; ++i) { ki[2 * i] = o->block_key[i]; ki[2 * i + 1] = i; }
+  qsort(ki, n, 16, cmp_u64idx);
+  for (uint64_t i = 0; i < n; ++i) {
+    unpack_key(ki[2 * i], block_xyz + 3 * i);
+    memcpy((char*)voxels + i * 4096, o->vox + ki[2 * i + 1] * 512, 4096);
+  }
+  free(ki);
+}
