@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=40, help="bounded CPU sample (frames)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--color", action="store_true", help="also fuse colour")
+    ap.add_argument("--simple-kernel", action="store_true", help="use the plain 2-voxel/thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,7 +209,8 @@ def main():
     frame_bytes = W * H * 2
 
     def make_volume(flags=0):
-        p = tsdf.default_params(batch_frames=args.batch, max_blocks=1 << 20, hash_slots=1 << 22, flags=flags)
+        p = tsdf.default_params(batch_frames=args.batch, max_blocks=1 << 20, hash_slots=1 << 22,
+                                flags=flags | (tsdf.KERNEL_SIMPLE if args.simple_kernel else 0))
         return tsdf.TsdfVolume(p, device=local, stream=torch.cuda.current_stream().cuda_stream)
 
     def barrier():

@@ -52,6 +52,8 @@ int scn_mesh_load(const char* path, float** xyz, uint64_t* n_verts, uint32_t** t
 /* flags for scn_segment_mesh */
 #define SCN_SEG_DEFAULT        0
 #define SCN_SEG_HOST_UNIONFIND 1   /* run the Kruskal / small-segment replay on the host instead of the GPU kernel */
+/* test hook (scn_segment_graph only): override introsort's depth limit 2*floor(log2 n) to reach the heap-sort fallback */
+#define SCN_SEG_TEST_DEPTH(d)  (((d) & 0xFF) << 8)
 
 /* segment() over raw arrays: seg_out[v] = root vertex id of v's segment, bit-identical to the
  * reference compiled with libstdc++ (incl. std::sort's unstable tie order). */

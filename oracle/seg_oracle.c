@@ -183,15 +183,17 @@ static void insertion_sort_guarded(oracle_edge* a, int64_t first, int64_t last) 
     } else linear_insert_unguarded(a, i);
   }
 }
-void oracle_seg_sort_edges(oracle_edge* a, int64_t n) {
+/* forced_depth > 0 overrides the depth limit (test hook to reach the heap-sort fallback) */
+void oracle_seg_sort_edges_depth(oracle_edge* a, int64_t n, int forced_depth) {
   if (n <= 0) return;
   int lg = 0; for (int64_t t = n; t > 1; t >>= 1) ++lg;            /* std::__lg */
-  introsort_loop(a, 0, n, 2 * lg);
+  introsort_loop(a, 0, n, forced_depth > 0 ? forced_depth : 2 * lg);
   if (n > 16) {
     insertion_sort_guarded(a, 0, 16);
     for (int64_t i = 16; i != n; ++i) linear_insert_unguarded(a, i);
   } else insertion_sort_guarded(a, 0, n);
 }
+void oracle_seg_sort_edges(oracle_edge* a, int64_t n) { oracle_seg_sort_edges_depth(a, n, 0); }
 
 /* ------------------------------------------------------------------ union-find + Kruskal */
 typedef struct { int32_t rank, p, size; } uf_elt;                  /* segmentator.cpp:18-22 */

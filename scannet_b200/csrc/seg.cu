@@ -1,0 +1,630 @@
+// Segmentator on B200 (sm_100a): Felzenszwalb–Huttenlocher graph segmentation of a triangle mesh
+// on vertex normals, bit-identical to /root/reference/Segmentator/segmentator.cpp compiled with
+// libstdc++ (GCC 13).
+//
+//   K1  k_face_normals / k_fill_csr / k_vertex_normals   segmentator.cpp:185-208
+//       The reference's vertex normal is a SEQUENTIAL running average in face-file order; each
+//       vertex replays its incident (face, corner) list in ascending order, so the float result is
+//       the same bit pattern.
+//   K2  k_edge_weights                                    segmentator.cpp:211-229
+//   K3  introsort emulation                               segmentator.cpp:67-72 (std::sort, comparator on w only)
+//       std::sort's tie order is observable in segIndices.  libstdc++'s
+//       introsort (bits/stl_algo.h:1848-1952) is reproduced exactly, in parallel:
+//         tier 1  level-synchronous over the recursion tree: every segment longer than kSmall is
+//                 partitioned by ALL CTAs with a parallel formulation of __unguarded_partition
+//                 (the k-th element >= pivot from the left swaps with the k-th element <= pivot from
+//                 the right while their positions have not crossed; two device-wide scans per level);
+//         tier 2  one thread per remaining segment (<= kSmall records) runs the literal sequential
+//                 introsort loop + insertion sort on its own contiguous records.
+//       The final __final_insertion_sort pass never moves a record across a partition boundary, so
+//       running it per segment is identical to running it over the whole array.
+//   S5-S7 Kruskal-with-threshold, small-segment merge and labelling (segmentator.cpp:71-91,236-250)
+//       are a strictly sequential, latency-bound replay (edge i's decision depends on the forest left
+//       by edges 0..i-1); they run on the host over the device-sorted records.
+// Float arithmetic: explicit round-to-nearest intrinsics, no contraction (-fmad=false), IEEE sqrt/div.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
+#include "scan.cuh"
+#include "scn_common.h"
+
+namespace {
+
+using scn::block_excl_scan;
+
+constexpr int kSmall = 256;          // tier-2 threshold (records)
+constexpr int kTile = 2048;          // tier-1 tile (records per CTA)
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = kTile / kTileThreads;   // 8
+
+struct Rec { float w; unsigned i; };
+static_assert(sizeof(Rec) == 8, "Rec must be 8 bytes");
+struct Edge12 { float w; int a, b; };
+static_assert(sizeof(Edge12) == 12, "edge record must be 12 bytes");
+
+// ------------------------------------------------------------------------------ K1: normals
+__global__ void k_face_normals(const float* __restrict__ xyz, const unsigned* __restrict__ tri, size_t nF,
+                               size_t nV, float4* __restrict__ fn, unsigned* __restrict__ deg) {
+  const size_t f = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (f >= nF) return;
+  const unsigned i1 = tri[3 * f], i2 = tri[3 * f + 1], i3 = tri[3 * f + 2];
+  const float* p1 = xyz + 3 * (size_t)i1; const float* p2 = xyz + 3 * (size_t)i2; const float* p3 = xyz + 3 * (size_t)i3;
+  const float ux = __fsub_rn(p2[0], p1[0]), uy = __fsub_rn(p2[1], p1[1]), uz = __fsub_rn(p2[2], p1[2]);
+  const float vx = __fsub_rn(p3[0], p1[0]), vy = __fsub_rn(p3[1], p1[1]), vz = __fsub_rn(p3[2], p1[2]);
+  float cx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
+  float cy = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
+  float cz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
+  const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+  cx = __fdiv_rn(cx, len); cy = __fdiv_rn(cy, len); cz = __fdiv_rn(cz, len);
+  fn[f] = make_float4(cx, cy, cz, 0.f);
+  atomicAdd(&deg[i1], 1u); atomicAdd(&deg[i2], 1u); atomicAdd(&deg[i3], 1u);
+}
+
+__global__ void k_fill_csr(const unsigned* __restrict__ tri, size_t nF, const unsigned* __restrict__ off,
+                           unsigned* __restrict__ cursor, unsigned* __restrict__ csr) {
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;       // corner id = 3f+k
+  if (c >= 3 * nF) return;
+  const unsigned v = tri[c];
+  const unsigned pos = atomicAdd(&cursor[v], 1u);
+  csr[off[v] + pos] = (unsigned)c;
+}
+
+__device__ void heap_sift_u32(unsigned* a, unsigned hole, unsigned len, unsigned val) {
+  for (;;) {
+    unsigned child = 2 * hole + 1;
+    if (child >= len) break;
+    if (child + 1 < len && a[child + 1] > a[child]) ++child;
+    if (a[child] <= val) break;
+    a[hole] = a[child]; hole = child;
+  }
+  a[hole] = val;
+}
+
+// one thread per vertex: sort its corner list ascending, replay the running average (segmentator.cpp:203-207)
+__global__ void k_vertex_normals(const unsigned* __restrict__ off, unsigned* __restrict__ csr,
+                                 const float4* __restrict__ fn, size_t nV, float* __restrict__ nrm) {
+  const size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const unsigned b = off[v], n = off[v + 1] - b;
+  unsigned loc[32];
+  unsigned* lst = csr + b;
+  const bool small = n <= 32;
+  if (small) {
+    for (unsigned i = 0; i < n; ++i) {                        // insertion sort into registers/local
+      const unsigned c = lst[i];
+      unsigned j = i;
+      while (j > 0 && loc[j - 1] > c) { loc[j] = loc[j - 1]; --j; }
+      loc[j] = c;
+    }
+  } else {                                                     // in-place heap sort in global memory
+    for (unsigned p = n / 2; p-- > 0;) heap_sift_u32(lst, p, n, lst[p]);
+    for (unsigned last = n; last > 1;) { --last; const unsigned t = lst[last]; lst[last] = lst[0]; heap_sift_u32(lst, 0, last, t); }
+  }
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  unsigned cnt = 0, pending = 0, prev_f = 0xFFFFFFFFu;
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned c = small ? loc[i] : lst[i];
+    const unsigned f = c / 3u;
+    if (f != prev_f) { cnt += pending; pending = 0; prev_f = f; }   // counts[] bumped only after the face's 3 lerps
+    const float4 q = fn[f];
+    const float t = __fdiv_rn(1.0f, __fadd_rn((float)cnt, 1.0f));
+    const float u = __fsub_rn(1.0f, t);
+    nx = __fadd_rn(__fmul_rn(t, q.x), __fmul_rn(u, nx));
+    ny = __fadd_rn(__fmul_rn(t, q.y), __fmul_rn(u, ny));
+    nz = __fadd_rn(__fmul_rn(t, q.z), __fmul_rn(u, nz));
+    ++pending;
+  }
+  nrm[3 * v] = nx; nrm[3 * v + 1] = ny; nrm[3 * v + 2] = nz;
+}
+
+// ------------------------------------------------------------------------------ K2: edge weights
+__device__ __forceinline__ void edge_ends(const unsigned* __restrict__ tri, size_t e, unsigned& a, unsigned& b) {
+  const size_t f = e / 3; const unsigned k = (unsigned)(e - 3 * f);
+  const unsigned i1 = tri[3 * f], i2 = tri[3 * f + 1], i3 = tri[3 * f + 2];
+  if (k == 0) { a = i1; b = i2; } else if (k == 1) { a = i1; b = i3; } else { a = i3; b = i2; }   // segmentator.cpp:198-200
+}
+
+__global__ void k_edge_weights(const float* __restrict__ xyz, const unsigned* __restrict__ tri,
+                               const float* __restrict__ nrm, size_t nE, Rec* __restrict__ rec) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= nE) return;
+  unsigned a, b;
+  edge_ends(tri, e, a, b);
+  const float* n1 = nrm + 3 * (size_t)a; const float* n2 = nrm + 3 * (size_t)b;
+  const float* p1 = xyz + 3 * (size_t)a; const float* p2 = xyz + 3 * (size_t)b;
+  float dx = __fsub_rn(p2[0], p1[0]), dy = __fsub_rn(p2[1], p1[1]), dz = __fsub_rn(p2[2], p1[2]);
+  const float dd = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  dx = __fdiv_rn(dx, dd); dy = __fdiv_rn(dy, dd); dz = __fdiv_rn(dz, dd);
+  const float n2x = n2[0], n2y = n2[1], n2z = n2[2];
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(n1[0], n2x), __fmul_rn(n1[1], n2y)), __fmul_rn(n1[2], n2z));
+  const float dot2 = __fadd_rn(__fadd_rn(__fmul_rn(n2x, dx), __fmul_rn(n2y, dy)), __fmul_rn(n2z, dz));
+  float ww = __fsub_rn(1.0f, dot);
+  if (dot2 > 0) ww = __fmul_rn(ww, ww);
+  rec[e].w = ww; rec[e].i = (unsigned)e;
+}
+
+__global__ void k_gather_edges(const Rec* __restrict__ rec, const unsigned* __restrict__ tri, size_t nE, Edge12* __restrict__ out) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE) return;
+  const Rec r = rec[j];
+  unsigned a, b;
+  edge_ends(tri, r.i, a, b);
+  out[j].w = r.w; out[j].a = (int)a; out[j].b = (int)b;
+}
+__global__ void k_gather_edges12(const Rec* __restrict__ rec, const Edge12* __restrict__ src, size_t nE, Edge12* __restrict__ out) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE) return;
+  out[j] = src[rec[j].i];
+}
+__global__ void k_rec_from_edges12(const Edge12* __restrict__ src, size_t nE, Rec* __restrict__ rec) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE) return;
+  rec[j].w = src[j].w; rec[j].i = (unsigned)j;
+}
+
+// ------------------------------------------------------------------------------ K3: libstdc++ introsort
+struct SortCtl {           // device-resident counters
+  unsigned n_next;         // large segments emitted for the next level
+  unsigned n_small;        // tier-2 segments
+  unsigned n_heap;         // depth-limit fallback segments
+  unsigned pad;
+};
+
+// sequential pieces (bits/stl_heap.h, bits/stl_algo.h), used by tier 2 and the heap fallback
+__device__ __forceinline__ bool rec_lt(const Rec& x, const Rec& y) { return x.w < y.w; }
+
+__device__ void d_adjust_heap(Rec* a, long hole, long len, Rec val) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (rec_lt(a[child], a[child - 1])) child--;
+    a[hole] = a[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    a[hole] = a[child - 1];
+    hole = child - 1;
+  }
+  long parent = (hole - 1) / 2;
+  while (hole > top && rec_lt(a[parent], val)) { a[hole] = a[parent]; hole = parent; parent = (hole - 1) / 2; }
+  a[hole] = val;
+}
+__device__ void d_heap_sort(Rec* a, long len) {            // __partial_sort(first, last, last)
+  if (len >= 2) for (long parent = (len - 2) / 2;; --parent) { d_adjust_heap(a, parent, len, a[parent]); if (parent == 0) break; }
+  for (long last = len; last > 1;) { --last; const Rec v = a[last]; a[last] = a[0]; d_adjust_heap(a, 0, last, v); }
+}
+__device__ __forceinline__ void d_swap(Rec* x, Rec* y) { const Rec t = *x; *x = *y; *y = t; }
+__device__ __forceinline__ void d_median_to_first(Rec* r, Rec* x, Rec* y, Rec* z) {   // __move_median_to_first
+  if (rec_lt(*x, *y)) {
+    if (rec_lt(*y, *z)) d_swap(r, y); else if (rec_lt(*x, *z)) d_swap(r, z); else d_swap(r, x);
+  } else if (rec_lt(*x, *z)) d_swap(r, x);
+  else if (rec_lt(*y, *z)) d_swap(r, z);
+  else d_swap(r, y);
+}
+__device__ long d_partition_pivot(Rec* a, long first, long last) {
+  const long mid = first + (last - first) / 2;
+  d_median_to_first(a + first, a + first + 1, a + mid, a + last - 1);
+  long lo = first + 1, hi = last;
+  const Rec piv = a[first];
+  for (;;) {
+    while (rec_lt(a[lo], piv)) ++lo;
+    --hi;
+    while (rec_lt(piv, a[hi])) --hi;
+    if (!(lo < hi)) return lo;
+    d_swap(a + lo, a + hi);
+    ++lo;
+  }
+}
+__device__ void d_insertion_sort(Rec* a, long n) {        // __insertion_sort on a whole (<= kSmall) segment
+  for (long i = 1; i < n; ++i) {
+    const Rec v = a[i];
+    if (rec_lt(v, a[0])) { for (long j = i; j > 0; --j) a[j] = a[j - 1]; a[0] = v; }
+    else { long j = i; while (rec_lt(v, a[j - 1])) { a[j] = a[j - 1]; --j; } a[j] = v; }
+  }
+}
+
+// tier 2: one thread per segment
+__global__ void k_sort_small(Rec* __restrict__ A, const unsigned* __restrict__ s_start, const unsigned* __restrict__ s_lend,
+                             unsigned n_small) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_small) return;
+  Rec* a = A + s_start[g];
+  const long len = (long)(s_lend[g] >> 8);
+  const int depth0 = (int)(s_lend[g] & 0xFFu);
+  // explicit stack for `__introsort_loop(cut, last, depth)` (recursion on the right part, loop on the left)
+  long st_first[64], st_last[64]; int st_depth[64]; int sp = 0;
+  long first = 0, last = len; int depth = depth0;
+  for (;;) {
+    while (last - first > 16) {
+      if (depth == 0) { d_heap_sort(a + first, last - first); break; }
+      --depth;
+      const long cut = d_partition_pivot(a, first, last);
+      // recurse right first in the reference; order between disjoint parts does not matter, push the right part
+      st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp;
+      last = cut;
+    }
+    if (sp == 0) break;
+    --sp; first = st_first[sp]; last = st_last[sp]; depth = st_depth[sp];
+  }
+  d_insertion_sort(a, len);
+}
+
+__global__ void k_sort_heap_fallback(Rec* __restrict__ A, const unsigned* __restrict__ h_start, const unsigned* __restrict__ h_end,
+                                     unsigned n_heap) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_heap) return;
+  d_heap_sort(A + h_start[g], (long)h_end[g] - (long)h_start[g]);
+}
+
+// tier 1 -----------------------------------------------------------------------------------------
+// per segment: median-of-3 to front (bits/stl_algo.h:1890-1900) and the number of tiles covering [s+1, e)
+__global__ void k_pivot(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+                        unsigned nseg, unsigned* __restrict__ tileCnt) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nseg) return;
+  const long first = segS[g], last = segE[g];
+  const long mid = first + (last - first) / 2;
+  d_median_to_first(A + first, A + first + 1, A + mid, A + last - 1);
+  tileCnt[g] = (unsigned)((last - first - 1 + kTile - 1) / kTile);
+}
+
+__device__ __forceinline__ unsigned find_seg(const unsigned* __restrict__ tileOff, unsigned nseg, unsigned tile) {
+  unsigned lo = 0, hi = nseg;                 // largest g with tileOff[g] <= tile
+  while (hi - lo > 1) { const unsigned m = (lo + hi) >> 1; if (tileOff[m] <= tile) lo = m; else hi = m; }
+  return lo;
+}
+
+struct TileCtx { unsigned g, s, e, t0; long base, end; float piv; };
+__device__ __forceinline__ TileCtx tile_ctx(const Rec* __restrict__ A, const unsigned* segS, const unsigned* segE,
+                                            const unsigned* tileOff, unsigned nseg) {
+  __shared__ TileCtx sc;
+  if (threadIdx.x == 0) {
+    TileCtx c;
+    c.g = find_seg(tileOff, nseg, blockIdx.x);
+    c.s = segS[c.g]; c.e = segE[c.g]; c.t0 = tileOff[c.g];
+    c.base = (long)c.s + 1 + (long)(blockIdx.x - c.t0) * kTile;
+    c.end = min((long)c.e, c.base + kTile);
+    c.piv = A[c.s].w;
+    sc = c;
+  }
+  __syncthreads();
+  return sc;
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+k_count(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+        const unsigned* __restrict__ tileOff, unsigned nseg, unsigned* __restrict__ tL, unsigned* __restrict__ tR) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+  unsigned nl = 0, nr = 0;
+  const long p0 = c.base + (long)threadIdx.x * kTileItems;
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i) {
+    const long p = p0 + i;
+    if (p < c.end) { const float w = A[p].w; nl += !(w < c.piv); nr += !(c.piv < w); }
+  }
+  unsigned totl, totr;
+  block_excl_scan(nl, &totl);
+  block_excl_scan(nr, &totr);
+  if (threadIdx.x == 0) { tL[blockIdx.x] = totl; tR[blockIdx.x] = totr; }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+k_scatter(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+          const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
+          const unsigned* __restrict__ tR, unsigned* __restrict__ Lpos, unsigned* __restrict__ Rpos) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+  const unsigned t1 = tileOff[c.g + 1];
+  const unsigned baseL = gL[blockIdx.x] - gL[c.t0];
+  const unsigned totR = gR[t1] - gR[c.t0];
+  const unsigned baseR = totR - (gR[blockIdx.x] - gR[c.t0]) - tR[blockIdx.x];     // right stoppers in later tiles
+  bool fl[kTileItems], fr[kTileItems];
+  unsigned nl = 0, nr = 0;
+  const long p0 = c.base + (long)threadIdx.x * kTileItems;
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i) {
+    const long p = p0 + i;
+    fl[i] = fr[i] = false;
+    if (p < c.end) { const float w = A[p].w; fl[i] = !(w < c.piv); fr[i] = !(c.piv < w); }
+    nl += fl[i]; nr += fr[i];
+  }
+  unsigned totr_tile;
+  unsigned exl = block_excl_scan(nl, nullptr);
+  unsigned exr = block_excl_scan(nr, &totr_tile);
+  // left stoppers: ascending rank from the left; right stoppers: rank counted from the right end
+  unsigned rl = baseL + exl;
+  unsigned after = totr_tile - exr - nr;                // right stoppers in later threads of this tile
+  unsigned rr_end = baseR + after + nr;                 // rank (from right) just past this thread's first item
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i) {
+    const long p = p0 + i;
+    if (fl[i]) { Lpos[c.s + rl] = (unsigned)p; ++rl; }
+    if (fr[i]) { --rr_end; Rpos[c.s + rr_end] = (unsigned)p; }
+  }
+}
+
+// swaps + cut.  k-th pair (Lpos[s+k], Rpos[s+k]) swaps iff Lpos < Rpos; cut = min(L[m], R[m-1]).
+__global__ void __launch_bounds__(kTileThreads)
+k_swap(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+       const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
+       const unsigned* __restrict__ Lpos, const unsigned* __restrict__ Rpos, unsigned* __restrict__ segCut) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+  const unsigned t1 = tileOff[c.g + 1];
+  const unsigned nL = gL[t1] - gL[c.t0], nR = gR[t1] - gR[c.t0];
+  const unsigned mn = min(nL, nR);
+  const unsigned k0 = (blockIdx.x - c.t0) * kTile + threadIdx.x * kTileItems;
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i) {
+    const unsigned k = k0 + i;
+    if (k >= mn) break;
+    const unsigned L = Lpos[c.s + k], R = Rpos[c.s + k];
+    const bool sw = L < R;
+    if (sw) { const Rec t = A[L]; A[L] = A[R]; A[R] = t; }
+    if (k == 0 && !sw) segCut[c.g] = L;                                        // m = 0
+    if (sw) {
+      const bool last = (k + 1 >= mn) || !(Lpos[c.s + k + 1] < Rpos[c.s + k + 1]);
+      if (last) {                                                              // m = k+1
+        const unsigned m = k + 1;
+        const unsigned lm = m < nL ? Lpos[c.s + m] : 0xFFFFFFFFu;
+        segCut[c.g] = min(lm, R);
+      }
+    }
+  }
+}
+
+__global__ void k_children(const unsigned* __restrict__ segS, const unsigned* __restrict__ segE, const unsigned* __restrict__ segD,
+                           const unsigned* __restrict__ segCut, unsigned nseg,
+                           unsigned* __restrict__ nS, unsigned* __restrict__ nE, unsigned* __restrict__ nD,
+                           unsigned* __restrict__ smStart, unsigned* __restrict__ smLenD,
+                           unsigned* __restrict__ hpStart, unsigned* __restrict__ hpEnd, SortCtl* __restrict__ ctl) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nseg) return;
+  const unsigned s = segS[g], e = segE[g], cut = segCut[g], d = segD[g] - 1;
+  const unsigned cs[2] = { s, cut }, ce[2] = { cut, e };
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const unsigned len = ce[c] - cs[c];
+    if (len <= 1) continue;
+    if (len <= (unsigned)kSmall) { const unsigned p = atomicAdd(&ctl->n_small, 1u); smStart[p] = cs[c]; smLenD[p] = (len << 8) | d; }
+    else if (d == 0) { const unsigned p = atomicAdd(&ctl->n_heap, 1u); hpStart[p] = cs[c]; hpEnd[p] = ce[c]; }
+    else { const unsigned p = atomicAdd(&ctl->n_next, 1u); nS[p] = cs[c]; nE[p] = ce[c]; nD[p] = d; }
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+  scn::fail(SCN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return SCN_ERR_CUDA; } } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <typename T> T* as() { return (T*)p; }
+  int alloc(size_t bytes) { if (bytes == 0) bytes = 16; return cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1; }
+};
+
+thread_local float g_timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local unsigned g_sort_launches = 0;
+
+// Sorts A[0..n) (device) exactly like libstdc++ std::sort with the `w`-only comparator.
+int device_introsort(Rec* A, size_t n, cudaStream_t st, int forced_depth = 0) {
+  g_sort_launches = 0;
+  if (n < 2) return SCN_OK;
+  if (n > 0x7FFFFFFFull) return scn::fail(SCN_ERR_ARG, "too many edges");
+  int lg = 0; for (size_t t = n; t > 1; t >>= 1) ++lg;
+  const unsigned depth0 = forced_depth > 0 ? (unsigned)forced_depth : 2u * (unsigned)lg;   // std::__lg(n) * 2
+  const size_t maxLarge = n / (kSmall + 1) + 2, maxSmall = n / 2 + 2, maxTiles = n / kTile + maxLarge + 2;
+  DevBuf bSeg[2], bCut, bTileCnt, bTileOff, bTL, bTR, bGL, bGR, bLpos, bRpos, bSm, bHp, bCtl, bScr;
+  for (int i = 0; i < 2; ++i) if (bSeg[i].alloc(maxLarge * 3 * 4)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc");
+  if (bCut.alloc(maxLarge * 4) || bTileCnt.alloc(maxLarge * 4) || bTileOff.alloc((maxLarge + 1) * 4) || bTL.alloc(maxTiles * 4) ||
+      bTR.alloc(maxTiles * 4) || bGL.alloc((maxTiles + 1) * 4) || bGR.alloc((maxTiles + 1) * 4) || bLpos.alloc(n * 4) ||
+      bRpos.alloc(n * 4) || bSm.alloc(maxSmall * 2 * 4) || bHp.alloc(maxLarge * 2 * 4) || bCtl.alloc(sizeof(SortCtl)) ||
+      bScr.alloc(scn::scan_scratch_elems(std::max(maxTiles, maxLarge)) * 4))
+    return scn::fail(SCN_ERR_CUDA, "cudaMalloc (sort workspace)");
+  unsigned* smStart = bSm.as<unsigned>(); unsigned* smLenD = smStart + maxSmall;
+  unsigned* hpStart = bHp.as<unsigned>(); unsigned* hpEnd = hpStart + maxLarge;
+  SortCtl* ctl = bCtl.as<SortCtl>();
+  CK(cudaMemsetAsync(ctl, 0, sizeof(SortCtl), st));
+  SortCtl h{};
+  unsigned nseg = 0;
+  int cur = 0;
+  if (n <= (size_t)kSmall) {
+    const unsigned s0 = 0, ld = ((unsigned)n << 8) | depth0;
+    CK(cudaMemcpyAsync(smStart, &s0, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(smLenD, &ld, 4, cudaMemcpyHostToDevice, st));
+    h.n_small = 1;
+  } else {
+    const unsigned init[3] = { 0u, (unsigned)n, depth0 };
+    unsigned* S = bSeg[0].as<unsigned>();
+    CK(cudaMemcpyAsync(S, &init[0], 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S + maxLarge, &init[1], 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S + 2 * maxLarge, &init[2], 4, cudaMemcpyHostToDevice, st));
+    nseg = 1;
+  }
+  while (nseg > 0) {
+    unsigned* S = bSeg[cur].as<unsigned>(); unsigned* E = S + maxLarge; unsigned* D = S + 2 * maxLarge;
+    unsigned* NS = bSeg[cur ^ 1].as<unsigned>(); unsigned* NE = NS + maxLarge; unsigned* ND = NS + 2 * maxLarge;
+    const unsigned gb = (nseg + 127) / 128;
+    k_pivot<<<gb, 128, 0, st>>>(A, S, E, nseg, bTileCnt.as<unsigned>());
+    g_sort_launches += 1 + scn::exclusive_scan_u32(bTileCnt.as<unsigned>(), bTileOff.as<unsigned>(), nseg, bScr.as<unsigned>(), st);
+    unsigned ntiles = 0;
+    CK(cudaMemcpyAsync(&ntiles, bTileOff.as<unsigned>() + nseg, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    k_count<<<ntiles, kTileThreads, 0, st>>>(A, S, E, bTileOff.as<unsigned>(), nseg, bTL.as<unsigned>(), bTR.as<unsigned>());
+    g_sort_launches += 1 + scn::exclusive_scan_u32(bTL.as<unsigned>(), bGL.as<unsigned>(), ntiles, bScr.as<unsigned>(), st);
+    g_sort_launches += scn::exclusive_scan_u32(bTR.as<unsigned>(), bGR.as<unsigned>(), ntiles, bScr.as<unsigned>(), st);
+    k_scatter<<<ntiles, kTileThreads, 0, st>>>(A, S, E, bTileOff.as<unsigned>(), nseg, bGL.as<unsigned>(), bGR.as<unsigned>(),
+                                                 bTR.as<unsigned>(), bLpos.as<unsigned>(), bRpos.as<unsigned>());
+    k_swap<<<ntiles, kTileThreads, 0, st>>>(A, S, E, bTileOff.as<unsigned>(), nseg, bGL.as<unsigned>(), bGR.as<unsigned>(),
+                                              bLpos.as<unsigned>(), bRpos.as<unsigned>(), bCut.as<unsigned>());
+    k_children<<<gb, 128, 0, st>>>(S, E, D, bCut.as<unsigned>(), nseg, NS, NE, ND, smStart, smLenD, hpStart, hpEnd, ctl);
+    g_sort_launches += 3;
+    CK(cudaMemcpyAsync(&h, ctl, sizeof(SortCtl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nseg = h.n_next;
+    const unsigned zero = 0;
+    CK(cudaMemcpyAsync(&ctl->n_next, &zero, 4, cudaMemcpyHostToDevice, st));
+    cur ^= 1;
+  }
+  if (h.n_heap) { k_sort_heap_fallback<<<(h.n_heap + 63) / 64, 64, 0, st>>>(A, hpStart, hpEnd, h.n_heap); ++g_sort_launches; }
+  if (h.n_small) { k_sort_small<<<(h.n_small + 63) / 64, 64, 0, st>>>(A, smStart, smLenD, h.n_small); ++g_sort_launches; }
+  CK(cudaGetLastError());
+  return SCN_OK;
+}
+
+// Sequential replay on the host (segmentator.cpp:71-91 Kruskal with adaptive threshold; :236-250).
+struct UfElt { int rank, p, size; };
+inline int uf_find(UfElt* u, int x) { int y = x; while (y != u[y].p) y = u[y].p; u[x].p = y; return y; }
+inline void uf_join(UfElt* u, int x, int y) {
+  if (u[x].rank > u[y].rank) { u[y].p = x; u[x].size += u[y].size; }
+  else { u[x].p = y; u[y].size += u[x].size; if (u[x].rank == u[y].rank) u[y].rank++; }
+}
+void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<UfElt>& u) {
+  u.resize(nV);
+  std::vector<float> thr(nV, c);
+  for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; }
+  for (size_t i = 0; i < nE; ++i) {
+    int a = uf_find(u.data(), e[i].a), b = uf_find(u.data(), e[i].b);
+    if (a != b && e[i].w <= thr[a] && e[i].w <= thr[b]) {
+      uf_join(u.data(), a, b);
+      a = uf_find(u.data(), a);
+      thr[a] = e[i].w + (c / (float)u[a].size);
+    }
+  }
+}
+void host_small_merge(const Edge12* e, size_t nE, int min_verts, std::vector<UfElt>& u) {
+  for (size_t j = 0; j < nE; ++j) {
+    const int a = uf_find(u.data(), e[j].a), b = uf_find(u.data(), e[j].b);
+    if (a != b && (u[a].size < min_verts || u[b].size < min_verts)) uf_join(u.data(), a, b);
+  }
+}
+
+struct Timer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  float lap() { auto t1 = std::chrono::steady_clock::now(); float ms = std::chrono::duration<float, std::milli>(t1 - t0).count(); t0 = t1; return ms; }
+};
+
+int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF, float kthr, int32_t min_verts,
+                 int32_t* seg_out, int flags, Edge12* edges_presort, Edge12* edges_sorted, float* normals_out,
+                 int32_t* roots_after_kruskal) {
+  (void)flags;
+  if ((!xyz && nV) || (!tri && nF) || !seg_out) return scn::fail(SCN_ERR_ARG, "null argument");
+  if (nV > 0x7FFFFFFFull || 3 * nF > 0x7FFFFFFFull) return scn::fail(SCN_ERR_ARG, "mesh too large for 32-bit ids");
+  for (int i = 0; i < 8; ++i) g_timings[i] = 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return scn::fail(SCN_ERR_CUDA, "no CUDA device: the Segmentator kernels have no CPU fallback");
+  Timer total, lapt;
+  const size_t nE = 3 * nF;
+  for (uint64_t i = 0; i < 3 * nF; ++i) if (tri[i] >= nV) return scn::fail(SCN_ERR_FORMAT, "face %llu references vertex %u >= %llu", (unsigned long long)(i / 3), tri[i], (unsigned long long)nV);
+  cudaStream_t st = nullptr;
+  DevBuf dXyz, dTri, dFn, dDeg, dOff, dCur, dCsr, dNrm, dRec, dE12, dScr;
+  if (dXyz.alloc(nV * 12) || dTri.alloc(nF * 12) || dFn.alloc(nF * 16) || dDeg.alloc((nV + 1) * 4) || dOff.alloc((nV + 2) * 4) ||
+      dCur.alloc((nV + 1) * 4) || dCsr.alloc(nE * 4) || dNrm.alloc(nV * 12) || dRec.alloc(nE * 8) || dE12.alloc(nE * 12) ||
+      dScr.alloc(scn::scan_scratch_elems(nV + 1) * 4))
+    return scn::fail(SCN_ERR_CUDA, "cudaMalloc (segmentator workspace)");
+  CK(cudaMemcpyAsync(dXyz.p, xyz, nV * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dTri.p, tri, nF * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(dDeg.p, 0, (nV + 1) * 4, st));
+  CK(cudaMemsetAsync(dCur.p, 0, (nV + 1) * 4, st));
+  CK(cudaStreamSynchronize(st));
+  g_timings[0] = lapt.lap();
+  const unsigned B = 256;
+  if (nF) {
+    k_face_normals<<<(unsigned)((nF + B - 1) / B), B, 0, st>>>(dXyz.as<float>(), dTri.as<unsigned>(), nF, nV, dFn.as<float4>(), dDeg.as<unsigned>());
+  }
+  scn::exclusive_scan_u32(dDeg.as<unsigned>(), dOff.as<unsigned>(), nV, dScr.as<unsigned>(), st);
+  if (nF) k_fill_csr<<<(unsigned)((nE + B - 1) / B), B, 0, st>>>(dTri.as<unsigned>(), nF, dOff.as<unsigned>(), dCur.as<unsigned>(), dCsr.as<unsigned>());
+  if (nV) k_vertex_normals<<<(unsigned)((nV + 127) / 128), 128, 0, st>>>(dOff.as<unsigned>(), dCsr.as<unsigned>(), dFn.as<float4>(), nV, dNrm.as<float>());
+  CK(cudaStreamSynchronize(st));
+  g_timings[1] = lapt.lap();
+  if (nE) k_edge_weights<<<(unsigned)((nE + B - 1) / B), B, 0, st>>>(dXyz.as<float>(), dTri.as<unsigned>(), dNrm.as<float>(), nE, dRec.as<Rec>());
+  CK(cudaStreamSynchronize(st));
+  g_timings[2] = lapt.lap();
+  if (normals_out && nV) CK(cudaMemcpy(normals_out, dNrm.p, nV * 12, cudaMemcpyDeviceToHost));
+  if (edges_presort && nE) {
+    k_gather_edges<<<(unsigned)((nE + B - 1) / B), B, 0, st>>>(dRec.as<Rec>(), dTri.as<unsigned>(), nE, dE12.as<Edge12>());
+    CK(cudaMemcpy(edges_presort, dE12.p, nE * 12, cudaMemcpyDeviceToHost));
+    lapt.lap();
+  }
+  int rc = device_introsort(dRec.as<Rec>(), nE, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  g_timings[3] = lapt.lap();
+  std::vector<Edge12> hE(nE);
+  if (nE) {
+    k_gather_edges<<<(unsigned)((nE + B - 1) / B), B, 0, st>>>(dRec.as<Rec>(), dTri.as<unsigned>(), nE, dE12.as<Edge12>());
+    CK(cudaMemcpy(hE.data(), dE12.p, nE * 12, cudaMemcpyDeviceToHost));
+  }
+  CK(cudaGetLastError());
+  g_timings[6] = lapt.lap();
+  if (edges_sorted && nE) memcpy(edges_sorted, hE.data(), nE * 12);
+  std::vector<UfElt> u;
+  host_kruskal(hE.data(), nE, nV, kthr, u);
+  g_timings[4] = lapt.lap();
+  if (roots_after_kruskal) for (size_t q = 0; q < nV; ++q) { int y = (int)q; while (y != u[y].p) y = u[y].p; roots_after_kruskal[q] = y; }
+  lapt.lap();
+  host_small_merge(hE.data(), nE, min_verts, u);
+  g_timings[5] = lapt.lap();
+  for (size_t q = 0; q < nV; ++q) seg_out[q] = uf_find(u.data(), (int)q);
+  g_timings[6] += lapt.lap();
+  g_timings[7] = total.lap();
+  return SCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scn_segment_mesh(const float* xyz, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces, float k_thresh,
+                     int32_t seg_min_verts, int32_t* seg_out, int flags) {
+  return segment_impl(xyz, n_verts, tri, n_faces, k_thresh, seg_min_verts, seg_out, flags, nullptr, nullptr, nullptr, nullptr);
+}
+
+int scn_segment_mesh_debug(const float* xyz, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces, float k_thresh,
+                           int32_t seg_min_verts, int32_t* seg_out, int flags, void* edges_presort, void* edges_sorted,
+                           float* vertex_normals, int32_t* roots_after_kruskal) {
+  return segment_impl(xyz, n_verts, tri, n_faces, k_thresh, seg_min_verts, seg_out, flags, (Edge12*)edges_presort,
+                      (Edge12*)edges_sorted, vertex_normals, roots_after_kruskal);
+}
+
+int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c, int32_t* roots_out, int32_t* sizes_out, int flags) {
+  if (n_verts < 0 || n_edges < 0 || (!edges && n_edges)) return scn::fail(SCN_ERR_ARG, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return scn::fail(SCN_ERR_CUDA, "no CUDA device");
+  Edge12* he = (Edge12*)edges;
+  for (int64_t i = 0; i < n_edges; ++i)
+    if (he[i].a < 0 || he[i].a >= n_verts || he[i].b < 0 || he[i].b >= n_verts) return scn::fail(SCN_ERR_ARG, "edge %lld endpoint out of range", (long long)i);
+  const size_t nE = (size_t)n_edges;
+  DevBuf dSrc, dDst, dRec;
+  if (dSrc.alloc(nE * 12) || dDst.alloc(nE * 12) || dRec.alloc(nE * 8)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc");
+  cudaStream_t st = nullptr;
+  if (nE) {
+    CK(cudaMemcpyAsync(dSrc.p, he, nE * 12, cudaMemcpyHostToDevice, st));
+    k_rec_from_edges12<<<(unsigned)((nE + 255) / 256), 256, 0, st>>>(dSrc.as<Edge12>(), nE, dRec.as<Rec>());
+  }
+  int rc = device_introsort(dRec.as<Rec>(), nE, st, (flags >> 8) & 0xFF);
+  if (rc) return rc;
+  if (nE) {
+    k_gather_edges12<<<(unsigned)((nE + 255) / 256), 256, 0, st>>>(dRec.as<Rec>(), dSrc.as<Edge12>(), nE, dDst.as<Edge12>());
+    CK(cudaMemcpy(he, dDst.p, nE * 12, cudaMemcpyDeviceToHost));
+  }
+  CK(cudaGetLastError());
+  std::vector<UfElt> u;
+  host_kruskal(he, nE, (size_t)n_verts, c, u);
+  for (int v = 0; v < n_verts; ++v) {
+    int y = v; while (y != u[y].p) y = u[y].p;
+    if (roots_out) roots_out[v] = y;
+    if (sizes_out) sizes_out[v] = u[y].size;
+  }
+  return SCN_OK;
+}
+
+int scn_segment_last_timings(float* ms8) {
+  if (!ms8) return scn::fail(SCN_ERR_ARG, "null argument");
+  for (int i = 0; i < 8; ++i) ms8[i] = g_timings[i];
+  return (int)g_sort_launches;
+}
+
+}  // extern "C"

@@ -48,6 +48,28 @@ def make_grid_mesh(nx: int = 250, ny: int = 200, seed: int = 0, spacing: float =
     return xyz, np.ascontiguousarray(tri)
 
 
+def make_feature_mesh(nx: int = 250, ny: int = 200, seed: int = 0, spacing: float = 0.02, noise: float = 0.0005):
+    """Height field with plateaus, hemispherical bumps, a ramp and a quantised (exactly flat, exact-tie)
+    third — gives tens to hundreds of segments at kThresh 0.01.  Same vertex/face layout as make_grid_mesh."""
+    rng = np.random.default_rng(seed)
+    xyz, tri = make_grid_mesh(nx, ny, seed=seed, spacing=spacing, shuffle_faces=True, flat_third=False, noise=0.0)
+    X = xyz[:, 0].astype(np.float64).reshape(ny, nx); Y = xyz[:, 1].astype(np.float64).reshape(ny, nx)
+    xs = np.arange(nx) * spacing; ys = np.arange(ny) * spacing
+    Z = np.where(X > xs[nx // 2], (X - xs[nx // 2]) * 0.5, 0.0) + 0.05 * np.sin(0.05 * Y / spacing)
+    for _ in range(min(200, max(4, (nx * ny) // 2500))):
+        cx, cy = rng.uniform(0, xs[-1]), rng.uniform(0, ys[-1]); r = rng.uniform(4, 14) * spacing
+        if rng.random() < 0.5:
+            h = rng.uniform(0.05, 0.3)
+            msk = (np.abs(X - cx) < r) & (np.abs(Y - cy) < r * rng.uniform(0.5, 1.5))
+            Z = np.where(msk, Z + h, Z)
+        else:
+            Z = Z + np.sqrt(np.maximum(r * r - ((X - cx) ** 2 + (Y - cy) ** 2), 0.0))
+    Z = Z + rng.normal(0.0, noise, Z.shape)
+    Z[:, : nx // 3] = np.round(Z[:, : nx // 3] / 0.25) * 0.25
+    xyz = xyz.copy(); xyz[:, 2] = Z.reshape(-1).astype(np.float32)
+    return xyz, tri
+
+
 def make_adversarial_mesh(seed: int = 0):
     """Small mesh exercising the reference's edge cases:
     a face repeating a vertex index, duplicated vertex positions (zero-length edge),

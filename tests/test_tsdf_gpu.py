@@ -59,7 +59,7 @@ def test_single_frame_api_equals_batch(built):
 
 def test_invalid_pose_and_ragged(built):
     """-inf poses are skipped (sensorData.h:382); width not a multiple of the 8x4 warp tile."""
-    p = tsdf.default_params(width=150, height=97, max_blocks=1 << 15, hash_slots=1 << 17, batch_frames=4)
+    p = tsdf.default_params(width=150, height=97, max_blocks=1 << 17, hash_slots=1 << 19, batch_frames=4)
     D, C, P, K = synth.make_frames(9, seed=6, width=150, height=97, loop_frames=90, invalid_pose_every=3, drop=0.1)
     g, o = run_both(p, D, C, P, K)
     assert_identical(g, o)
@@ -93,6 +93,14 @@ def test_full_resolution_frames(built):
     assert_identical(g, o)
     # geometric sanity (size-independent property): |sdf| <= trunc at the observed depth range
     assert np.abs(g[1]["sdf"]).max() <= 0.02 + 0.01 * 6.0 + 1e-6
+
+
+def test_simple_kernel_variant(built):
+    """the plain 2-voxels-per-thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE) gives the same bits"""
+    p = tsdf.default_params(width=160, height=120, max_blocks=1 << 15, hash_slots=1 << 17, batch_frames=5,
+                            flags=tsdf.KERNEL_SIMPLE)
+    D, C, P, K = synth.make_frames(6, seed=9, width=160, height=120, loop_frames=150, noise_mm=1.0)
+    assert_identical(*run_both(p, D, C, P, K))
 
 
 def test_capacity_error_is_reported(built):
