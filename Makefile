@@ -9,7 +9,8 @@ LIBDIR   := scannet_b200/lib
 BINDIR   := scannet_b200/bin
 OBJDIR   := build/obj
 SRCS     := $(wildcard $(CSRC)/*.cu)
-OBJS     := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+CPPSRCS  := $(wildcard $(CSRC)/*.cpp)
+OBJS     := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.cpp.o,$(CPPSRCS))
 LIB      := $(LIBDIR)/libscannet_b200.so
 TOOLS    := $(patsubst scannet_b200/tools/%_main.cpp,$(BINDIR)/%,$(wildcard scannet_b200/tools/*_main.cpp))
 
@@ -19,6 +20,9 @@ tools: $(TOOLS)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/scannet_b200.h | $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scannet_b200.h | $(OBJDIR)
+	/usr/bin/g++ -O2 -std=c++17 -fPIC -Wall -Wno-unused-function -Wno-misleading-indentation -ffp-contract=off -c $< -o $@
 
 $(LIB): $(OBJS) | $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ccbin /usr/bin/g++ -cudart static

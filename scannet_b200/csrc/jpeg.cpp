@@ -1,0 +1,319 @@
+// Baseline JPEG -> RGB8 for `.sens` colour frames (TYPE_JPEG), host side.
+//
+// The reference decodes colour through stb_image v2.08 (vendored third-party code at
+// /root/reference/SensReader/c++/src/sensorData/stb_image.h, called from sensorData.h:609-616 with
+// 3 requested channels).  JPEG decoding is only defined up to IDCT / up-sampling / colour-conversion
+// rounding, so to return the SAME BYTES this decoder restates stb's published numerics:
+//   * integer "islow" IDCT, 12-bit constants, column pass keeps 2 extra bits (stb_image.h:1928-2027)
+//   * chroma up-sampling: h2 / v2 = (3*near + far + 2) >> 2, h2v2 = (9,3,3,1)/16 with +8 (stb_image.h:2871-2925),
+//     any other ratio nearest-neighbour (:3046-3056); row pairing by the ystep state machine (:3209-3225)
+//   * YCbCr -> RGB in 20-bit fixed point with the masked Cb term (stb_image.h:3091-3118)
+//   * coefficients truncated to int16 after de-quantisation (:1735,1764)
+// Structure (marker parser, canonical Huffman decoder, plane layout) is this repo's own.
+// Supported: SOF0/SOF1 8-bit, 1 or 3 components, interleaved and non-interleaved scans, restart markers.
+// Progressive (SOF2) files are rejected with SCN_ERR_UNSUPPORTED.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "scn_common.h"
+
+namespace {
+
+const uint8_t kZig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11,4,5,12,19,26,33,40,48,41,34,27,20,13,6,7,14,21,28,35,42,49,56,57,50,43,36,
+                               29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63,
+                               63,63,63,63,63,63,63,63,63,63,63,63,63,63,63};
+
+struct HuffTab {
+  bool present = false;
+  int maxcode[18]; int valptr[17]; int mincode[17]; uint8_t vals[256];
+  bool build(const uint8_t* counts, const uint8_t* symbols, int nsym) {
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; ++l) {
+      valptr[l] = k; mincode[l] = code;
+      code += counts[l - 1]; k += counts[l - 1];
+      if (code > (1 << l)) return false;
+      maxcode[l] = counts[l - 1] ? code - 1 : -1;
+      code <<= 1;
+    }
+    maxcode[17] = 0x7FFFFFFF;
+    memcpy(vals, symbols, (size_t)nsym);
+    present = true;
+    return true;
+  }
+};
+
+struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0, x = 0, y = 0, w2 = 0, h2 = 0; std::vector<uint8_t> data; };
+
+struct Bits {
+  const uint8_t* p; size_t n, pos; uint32_t buf = 0; int cnt = 0; bool hit_marker = false;
+  void fill() {
+    while (cnt <= 24) {
+      uint32_t b = 0;
+      if (!hit_marker && pos < n) {
+        b = p[pos];
+        if (b == 0xFF) {
+          const uint8_t nx = pos + 1 < n ? p[pos + 1] : 0xD9;
+          if (nx == 0) pos += 2; else { hit_marker = true; b = 0; }
+        } else ++pos;
+      }
+      buf |= b << (24 - cnt); cnt += 8;
+    }
+  }
+  int get(int k) { if (k == 0) return 0; if (cnt < k) fill(); const int v = (int)(buf >> (32 - k)); buf <<= k; cnt -= k; return v; }
+  int decode(const HuffTab& h) {
+    if (cnt < 16) fill();
+    int code = 0;
+    for (int l = 1; l <= 16; ++l) {
+      code = (code << 1) | (int)(buf >> 31); buf <<= 1; --cnt;
+      if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+    }
+    return -1;
+  }
+  void reset() { buf = 0; cnt = 0; hit_marker = false; }
+};
+
+inline int extend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
+inline uint8_t clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x; }
+
+#define F2F(x) ((int)(((x) * 4096 + 0.5)))
+#define IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                      \
+  int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                            \
+  p2 = s2; p3 = s6;                                                                  \
+  p1 = (p2 + p3) * F2F(0.5411961f);                                                  \
+  t2 = p1 + p3 * F2F(-1.847759065f);                                                 \
+  t3 = p1 + p2 * F2F(0.765366865f);                                                  \
+  p2 = s0; p3 = s4;                                                                  \
+  t0 = (p2 + p3) << 12; t1 = (p2 - p3) << 12;                                        \
+  x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2;                            \
+  t0 = s7; t1 = s5; t2 = s3; t3 = s1;                                                \
+  p3 = t0 + t2; p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2;                            \
+  p5 = (p3 + p4) * F2F(1.175875602f);                                                \
+  t0 = t0 * F2F(0.298631336f); t1 = t1 * F2F(2.053119869f);                          \
+  t2 = t2 * F2F(3.072711026f); t3 = t3 * F2F(1.501321110f);                          \
+  p1 = p5 + p1 * F2F(-0.899976223f); p2 = p5 + p2 * F2F(-2.562915447f);              \
+  p3 = p3 * F2F(-1.961570560f); p4 = p4 * F2F(-0.390180644f);                        \
+  t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
+
+void idct8x8(uint8_t* out, int stride, const short* d) {
+  int val[64];
+  for (int i = 0; i < 8; ++i) {
+    const short* c = d + i; int* v = val + i;
+    if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
+      const int dc = c[0] << 2;
+      v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
+    } else {
+      IDCT_1D(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56])
+      x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+      v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10; v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
+      v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10; v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+    }
+  }
+  for (int i = 0; i < 8; ++i) {
+    const int* v = val + 8 * i; uint8_t* o = out + (size_t)i * stride;
+    IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
+    const int bias = 65536 + (128 << 17);
+    x0 += bias; x1 += bias; x2 += bias; x3 += bias;
+    o[0] = clamp8((x0 + t3) >> 17); o[7] = clamp8((x0 - t3) >> 17); o[1] = clamp8((x1 + t2) >> 17); o[6] = clamp8((x1 - t2) >> 17);
+    o[2] = clamp8((x2 + t1) >> 17); o[5] = clamp8((x2 - t1) >> 17); o[3] = clamp8((x3 + t0) >> 17); o[4] = clamp8((x3 - t0) >> 17);
+  }
+}
+
+const uint8_t* up_h2(uint8_t* out, const uint8_t* in, int w) {
+  if (w == 1) { out[0] = out[1] = in[0]; return out; }
+  out[0] = in[0]; out[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+  int i;
+  for (i = 1; i < w - 1; ++i) { const int n = 3 * in[i] + 2; out[i * 2] = (uint8_t)((n + in[i - 1]) >> 2); out[i * 2 + 1] = (uint8_t)((n + in[i + 1]) >> 2); }
+  out[i * 2] = (uint8_t)((in[w - 2] * 3 + in[w - 1] + 2) >> 2); out[i * 2 + 1] = in[w - 1];
+  return out;
+}
+const uint8_t* up_v2(uint8_t* out, const uint8_t* nr, const uint8_t* fr, int w) {
+  for (int i = 0; i < w; ++i) out[i] = (uint8_t)((3 * nr[i] + fr[i] + 2) >> 2);
+  return out;
+}
+const uint8_t* up_hv2(uint8_t* out, const uint8_t* nr, const uint8_t* fr, int w) {
+  if (w == 1) { out[0] = out[1] = (uint8_t)((3 * nr[0] + fr[0] + 2) >> 2); return out; }
+  int t1 = 3 * nr[0] + fr[0], t0;
+  out[0] = (uint8_t)((t1 + 2) >> 2);
+  for (int i = 1; i < w; ++i) { t0 = t1; t1 = 3 * nr[i] + fr[i]; out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4); out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4); }
+  out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
+  return out;
+}
+const uint8_t* up_generic(uint8_t* out, const uint8_t* in, int w, int hs) {
+  for (int i = 0; i < w; ++i) for (int j = 0; j < hs; ++j) out[i * hs + j] = in[i];
+  return out;
+}
+
+#define FIX20(x) (((int)((x) * 4096.0f + 0.5f)) << 8)
+inline void ycc_to_rgb(uint8_t* out, int y, int cbv, int crv) {
+  const int yf = (y << 20) + (1 << 19), cr = crv - 128, cb = cbv - 128;
+  int r = yf + cr * FIX20(1.40200f);
+  int g = yf + (cr * -FIX20(0.71414f)) + ((cb * -FIX20(0.34414f)) & 0xffff0000);
+  int b = yf + cb * FIX20(1.77200f);
+  r >>= 20; g >>= 20; b >>= 20;
+  out[0] = clamp8(r); out[1] = clamp8(g); out[2] = clamp8(b);
+}
+
+}  // namespace
+
+namespace scn {
+
+int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out) {
+  if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return fail(SCN_ERR_FORMAT, "not a JPEG (no SOI)");
+  uint8_t quant[4][64]; bool have_q[4] = {false, false, false, false};
+  HuffTab hdc[4], hac[4];
+  Comp comp[3]; int ncomp = 0, W = 0, H = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0, restart = 0;
+  bool have_frame = false;
+  size_t pos = 2;
+  for (;;) {
+    while (pos < n && d[pos] != 0xFF) ++pos;
+    while (pos < n && d[pos] == 0xFF) ++pos;
+    if (pos >= n) break;
+    const int m = d[pos++];
+    if (m == 0xD9) break;
+    if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+    if (pos + 2 > n) return fail(SCN_ERR_FORMAT, "truncated JPEG");
+    const size_t len = ((size_t)d[pos] << 8) | d[pos + 1];
+    if (len < 2 || pos + len > n) return fail(SCN_ERR_FORMAT, "bad JPEG segment length");
+    const uint8_t* s = d + pos + 2; size_t sl = len - 2;
+    if (m == 0xDB) {
+      while (sl > 0) {
+        const int pq = s[0] >> 4, tq = s[0] & 15;
+        if (pq != 0) return fail(SCN_ERR_UNSUPPORTED, "16-bit quantisation tables are not supported (as in stb_image)");
+        if (tq > 3 || sl < 65) return fail(SCN_ERR_FORMAT, "bad DQT");
+        for (int i = 0; i < 64; ++i) quant[tq][kZig[i]] = s[1 + i];
+        have_q[tq] = true; s += 65; sl -= 65;
+      }
+    } else if (m == 0xC4) {
+      while (sl > 0) {
+        if (sl < 17) return fail(SCN_ERR_FORMAT, "bad DHT");
+        const int tc = s[0] >> 4, th = s[0] & 15; int tot = 0;
+        for (int i = 0; i < 16; ++i) tot += s[1 + i];
+        if (tc > 1 || th > 3 || tot > 256 || sl < (size_t)(17 + tot)) return fail(SCN_ERR_FORMAT, "bad DHT");
+        if (!(tc ? hac[th] : hdc[th]).build(s + 1, s + 17, tot)) return fail(SCN_ERR_FORMAT, "bad code lengths");
+        s += 17 + tot; sl -= 17 + tot;
+      }
+    } else if (m == 0xDD) { if (sl < 2) return fail(SCN_ERR_FORMAT, "bad DRI"); restart = (s[0] << 8) | s[1]; }
+    else if (m == 0xC2) return fail(SCN_ERR_UNSUPPORTED, "progressive JPEG is not supported");
+    else if (m == 0xC0 || m == 0xC1) {
+      if (sl < 6 || s[0] != 8) return fail(SCN_ERR_UNSUPPORTED, "only 8-bit JPEG");
+      H = (s[1] << 8) | s[2]; W = (s[3] << 8) | s[4]; ncomp = s[5];
+      if ((ncomp != 1 && ncomp != 3) || sl < (size_t)(6 + 3 * ncomp) || W == 0 || H == 0) return fail(SCN_ERR_FORMAT, "bad SOF");
+      for (int i = 0; i < ncomp; ++i) {
+        comp[i].id = s[6 + 3 * i]; comp[i].h = s[7 + 3 * i] >> 4; comp[i].v = s[7 + 3 * i] & 15; comp[i].tq = s[8 + 3 * i];
+        if (!comp[i].h || comp[i].h > 4 || !comp[i].v || comp[i].v > 4 || comp[i].tq > 3) return fail(SCN_ERR_FORMAT, "bad SOF component");
+        hmax = std::max(hmax, comp[i].h); vmax = std::max(vmax, comp[i].v);
+      }
+      mcux = (W + 8 * hmax - 1) / (8 * hmax); mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+      for (int i = 0; i < ncomp; ++i) {
+        comp[i].x = (W * comp[i].h + hmax - 1) / hmax; comp[i].y = (H * comp[i].v + vmax - 1) / vmax;
+        comp[i].w2 = mcux * comp[i].h * 8; comp[i].h2 = mcuy * comp[i].v * 8;
+        comp[i].data.assign((size_t)comp[i].w2 * comp[i].h2 + 15, 0);
+      }
+      have_frame = true;
+    } else if (m == 0xDA) {
+      if (!have_frame) return fail(SCN_ERR_FORMAT, "SOS before SOF");
+      const int ns = s[0];
+      if (ns < 1 || ns > ncomp || sl < (size_t)(1 + 2 * ns + 3)) return fail(SCN_ERR_FORMAT, "bad SOS");
+      int order[3];
+      for (int i = 0; i < ns; ++i) {
+        int which = -1;
+        for (int c = 0; c < ncomp; ++c) if (comp[c].id == s[1 + 2 * i]) which = c;
+        if (which < 0) return fail(SCN_ERR_FORMAT, "bad SOS component");
+        comp[which].td = s[2 + 2 * i] >> 4; comp[which].ta = s[2 + 2 * i] & 15;
+        if (comp[which].td > 3 || comp[which].ta > 3 || !hdc[comp[which].td].present || !hac[comp[which].ta].present || !have_q[comp[which].tq])
+          return fail(SCN_ERR_FORMAT, "scan references a missing table");
+        order[i] = which;
+      }
+      Bits br{d, n, pos + len};
+      for (int c = 0; c < ncomp; ++c) comp[c].dc_pred = 0;
+      int todo = restart ? restart : 0x7fffffff;
+      short blk[64];
+      auto decode_block = [&](Comp& c, int bx, int by) -> bool {
+        memset(blk, 0, sizeof(blk));
+        const int t = br.decode(hdc[c.td]);
+        if (t < 0 || t > 16) return false;
+        const int diff = t ? extend(br.get(t), t) : 0;
+        c.dc_pred += diff;
+        blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
+        for (int k = 1; k < 64;) {
+          const int rs = br.decode(hac[c.ta]);
+          if (rs < 0) return false;
+          const int sz = rs & 15, r = rs >> 4;
+          if (sz == 0) { if (rs != 0xF0) break; k += 16; }
+          else { k += r; const int z = kZig[k++]; blk[z] = (short)(extend(br.get(sz), sz) * quant[c.tq][z]); }
+        }
+        idct8x8(c.data.data() + (size_t)c.w2 * by * 8 + (size_t)bx * 8, c.w2, blk);
+        return true;
+      };
+      auto handle_restart = [&]() {
+        if (--todo <= 0) {
+          // byte-align, expect RSTn
+          br.reset();
+          size_t q = br.pos;
+          while (q + 1 < n && !(d[q] == 0xFF && d[q + 1] >= 0xD0 && d[q + 1] <= 0xD7)) { if (d[q] == 0xFF && d[q + 1] != 0 && d[q + 1] != 0xFF) return false; ++q; }
+          if (q + 1 >= n) return false;
+          br.pos = q + 2;
+          for (int c = 0; c < ncomp; ++c) comp[c].dc_pred = 0;
+          todo = restart ? restart : 0x7fffffff;
+        }
+        return true;
+      };
+      bool ended = false;
+      if (ns == 1) {
+        Comp& c = comp[order[0]];
+        const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+        for (int j = 0; j < bh && !ended; ++j) for (int i = 0; i < bw; ++i) {
+          if (!decode_block(c, i, j)) return fail(SCN_ERR_FORMAT, "bad huffman code");
+          if (!handle_restart()) { ended = true; break; }
+        }
+      } else {
+        for (int j = 0; j < mcuy && !ended; ++j) for (int i = 0; i < mcux; ++i) {
+          for (int k = 0; k < ns; ++k) { Comp& c = comp[order[k]];
+            for (int y = 0; y < c.v; ++y) for (int x = 0; x < c.h; ++x)
+              if (!decode_block(c, i * c.h + x, j * c.v + y)) return fail(SCN_ERR_FORMAT, "bad huffman code"); }
+          if (!handle_restart()) { ended = true; break; }
+        }
+      }
+      // continue the marker scan after the entropy-coded data
+      pos = br.pos;
+      while (pos + 1 < n && !(d[pos] == 0xFF && d[pos + 1] != 0 && !(d[pos + 1] >= 0xD0 && d[pos + 1] <= 0xD7) && d[pos + 1] != 0xFF)) ++pos;
+      continue;
+    }
+    pos += len;
+  }
+  if (!have_frame) return fail(SCN_ERR_FORMAT, "no frame in JPEG");
+  if ((uint32_t)W != want_w || (uint32_t)H != want_h) return fail(SCN_ERR_FORMAT, "JPEG is %dx%d, header says %ux%u", W, H, want_w, want_h);
+  // up-sample + colour convert, row by row (stb_image.h:3166-3250)
+  struct Res { int hs, vs, ystep, wl, ypos; const uint8_t *l0, *l1; std::vector<uint8_t> buf; } rs[3];
+  for (int k = 0; k < ncomp; ++k) {
+    rs[k].hs = hmax / comp[k].h; rs[k].vs = vmax / comp[k].v; rs[k].ystep = rs[k].vs >> 1;
+    rs[k].wl = (W + rs[k].hs - 1) / rs[k].hs; rs[k].ypos = 0; rs[k].l0 = rs[k].l1 = comp[k].data.data();
+    rs[k].buf.assign((size_t)W + 16 + 8 * hmax, 0);
+  }
+  for (int j = 0; j < H; ++j) {
+    const uint8_t* row[3];
+    for (int k = 0; k < ncomp; ++k) {
+      Res& r = rs[k];
+      const bool bot = r.ystep >= (r.vs >> 1);
+      const uint8_t* nr = bot ? r.l1 : r.l0; const uint8_t* fr = bot ? r.l0 : r.l1;
+      if (r.hs == 1 && r.vs == 1) row[k] = nr;
+      else if (r.hs == 1 && r.vs == 2) row[k] = up_v2(r.buf.data(), nr, fr, r.wl);
+      else if (r.hs == 2 && r.vs == 1) row[k] = up_h2(r.buf.data(), nr, r.wl);
+      else if (r.hs == 2 && r.vs == 2) row[k] = up_hv2(r.buf.data(), nr, fr, r.wl);
+      else row[k] = up_generic(r.buf.data(), nr, r.wl, r.hs);
+      if (++r.ystep >= r.vs) { r.ystep = 0; r.l0 = r.l1; if (++r.ypos < comp[k].y) r.l1 += comp[k].w2; }
+    }
+    uint8_t* o = out + (size_t)j * W * 3;
+    if (ncomp == 3) for (int i = 0; i < W; ++i) ycc_to_rgb(o + 3 * i, row[0][i], row[1][i], row[2][i]);
+    else for (int i = 0; i < W; ++i) o[3 * i] = o[3 * i + 1] = o[3 * i + 2] = row[0][i];
+  }
+  return SCN_OK;
+}
+
+int png_decode_rgb8(const uint8_t*, size_t, uint32_t, uint32_t, uint8_t*) {
+  return fail(SCN_ERR_UNSUPPORTED, "PNG colour frames are not supported (ScanNet .sens files store JPEG, Converter/main.cpp:37)");
+}
+
+}  // namespace scn

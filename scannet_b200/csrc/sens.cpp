@@ -1,0 +1,523 @@
+// SensReader: the `.sens` v4 RGB-D container (host side, C++), mirroring ml::SensorData
+// (/root/reference/SensReader/c++/src/sensorData.h:285-1936) behind the C ABI.
+//
+//   file layout            sensorData.h:1058-1074 (header), :733-754 (RGBDFrame), :786-833 (IMUFrame)
+//   depth decode           :693-730  TYPE_RAW_USHORT / TYPE_ZLIB_USHORT (the reference inflates with
+//                          stb's zlib decoder; any conforming inflate yields the same bytes — ours is below)
+//   colour decode          :600-646  TYPE_RAW / JPEG / PNG (see jpeg.cpp)
+//   writer                 :888-929 initDefault/addFrame, :648-691 compressDepth, :1101-1109 saveToFile
+//   saveToImages / PGM     :1342-1466, savePoseFile :1706-1714, operator<< :1941-1955
+// Errors never cross the boundary as exceptions: every entry point returns a status.
+#include <sys/stat.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "scn_common.h"
+
+namespace scn {
+int jpeg_decode_rgb8(const uint8_t* data, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out);   // jpeg.cpp
+int png_decode_rgb8(const uint8_t* data, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out);    // jpeg.cpp
+int zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t size_hint);
+void zlib_deflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out);
+}  // namespace scn
+
+// ------------------------------------------------------------------------------ inflate (RFC 1950/1951)
+namespace {
+
+struct BitReader {
+  const uint8_t* p; size_t n, pos = 0; uint32_t buf = 0; int cnt = 0; bool bad = false;
+  BitReader(const uint8_t* d, size_t len) : p(d), n(len) {}
+  uint32_t bits(int k) {
+    while (cnt < k) { if (pos >= n) { bad = true; return 0; } buf |= (uint32_t)p[pos++] << cnt; cnt += 8; }
+    const uint32_t v = buf & ((k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1)); buf >>= k; cnt -= k; return v;
+  }
+};
+struct Huff {
+  uint16_t count[16]; uint16_t symbol[288];
+  void build(const uint8_t* len, int n) {
+    memset(count, 0, sizeof(count));
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    count[0] = 0;
+    uint16_t offs[16]; offs[1] = 0;
+    for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
+    for (int i = 0; i < n; ++i) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+  }
+  int decode(BitReader& br) const {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; ++l) {
+      code |= (int)br.bits(1);
+      if (br.bad) return -1;
+      const int c = count[l];
+      if (code - c < first) return symbol[index + (code - first)];
+      index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+  }
+};
+const uint16_t kLenBase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+const uint8_t kLenExtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+const uint16_t kDistBase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+const uint8_t kDistExtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+
+}  // namespace
+
+int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t size_hint) {
+  out.clear();
+  if (size_hint) out.reserve(size_hint);
+  if (n < 6) return -1;
+  if ((src[0] & 0x0F) != 8 || ((src[0] << 8) | src[1]) % 31 != 0 || (src[1] & 0x20)) return -1;
+  BitReader br(src + 2, n - 2);
+  Huff lit, dist;
+  for (;;) {
+    const uint32_t final = br.bits(1), type = br.bits(2);
+    if (br.bad) return -1;
+    if (type == 0) {
+      br.buf = 0; br.cnt = 0;
+      if (br.pos + 4 > br.n) return -1;
+      const uint32_t len = br.p[br.pos] | (br.p[br.pos + 1] << 8), nlen = br.p[br.pos + 2] | (br.p[br.pos + 3] << 8);
+      br.pos += 4;
+      if ((len ^ 0xFFFF) != nlen || br.pos + len > br.n) return -1;
+      out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
+      br.pos += len;
+    } else if (type == 1 || type == 2) {
+      uint8_t lens[320];
+      if (type == 1) {
+        int i = 0;
+        for (; i < 144; ++i) lens[i] = 8; for (; i < 256; ++i) lens[i] = 9; for (; i < 280; ++i) lens[i] = 7; for (; i < 288; ++i) lens[i] = 8;
+        lit.build(lens, 288);
+        for (i = 0; i < 30; ++i) lens[i] = 5;
+        dist.build(lens, 30);
+      } else {
+        const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+        if (br.bad || nlen > 286 || ndist > 30) return -1;
+        static const uint8_t order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+        uint8_t cl[19]; memset(cl, 0, sizeof(cl));
+        for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
+        Huff clh; clh.build(cl, 19);
+        int idx = 0;
+        while (idx < nlen + ndist) {
+          const int sym = clh.decode(br);
+          if (sym < 0) return -1;
+          if (sym < 16) lens[idx++] = (uint8_t)sym;
+          else {
+            int rep, val = 0;
+            if (sym == 16) { if (idx == 0) return -1; val = lens[idx - 1]; rep = 3 + (int)br.bits(2); }
+            else if (sym == 17) rep = 3 + (int)br.bits(3);
+            else rep = 11 + (int)br.bits(7);
+            if (idx + rep > nlen + ndist) return -1;
+            while (rep--) lens[idx++] = (uint8_t)val;
+          }
+        }
+        lit.build(lens, nlen);
+        dist.build(lens + nlen, ndist);
+      }
+      for (;;) {
+        const int sym = lit.decode(br);
+        if (sym < 0) return -1;
+        if (sym < 256) out.push_back((uint8_t)sym);
+        else if (sym == 256) break;
+        else {
+          const int li = sym - 257;
+          if (li >= 29) return -1;
+          const int len = kLenBase[li] + (int)br.bits(kLenExtra[li]);
+          const int ds = dist.decode(br);
+          if (ds < 0 || ds >= 30) return -1;
+          const size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
+          if (br.bad || d > out.size()) return -1;
+          const size_t start = out.size() - d;
+          for (int i = 0; i < len; ++i) out.push_back(out[start + i]);
+        }
+      }
+    } else return -1;
+    if (final) break;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ deflate (fixed Huffman + LZ77 hash chains)
+namespace {
+struct BitWriter {
+  std::vector<uint8_t>& o; uint32_t buf = 0; int cnt = 0;
+  explicit BitWriter(std::vector<uint8_t>& out) : o(out) {}
+  void put(uint32_t v, int k) { buf |= v << cnt; cnt += k; while (cnt >= 8) { o.push_back((uint8_t)buf); buf >>= 8; cnt -= 8; } }
+  void put_rev(uint32_t code, int k) { uint32_t r = 0; for (int i = 0; i < k; ++i) r |= ((code >> i) & 1u) << (k - 1 - i); put(r, k); }
+  void flush() { if (cnt) { o.push_back((uint8_t)buf); buf = 0; cnt = 0; } }
+};
+void put_litlen(BitWriter& bw, int sym) {
+  if (sym < 144) bw.put_rev(0x30 + sym, 8);
+  else if (sym < 256) bw.put_rev(0x190 + (sym - 144), 9);
+  else if (sym < 280) bw.put_rev(sym - 256, 7);
+  else bw.put_rev(0xC0 + (sym - 280), 8);
+}
+}  // namespace
+
+void scn::zlib_deflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+  out.clear();
+  out.push_back(0x78); out.push_back(0x5E);
+  BitWriter bw(out);
+  bw.put(1, 1); bw.put(1, 2);                                   // final block, fixed Huffman
+  const int HB = 15; std::vector<int32_t> head(1 << HB, -1), prev(n ? n : 1, -1);
+  auto hash = [&](size_t i) { return (uint32_t)((src[i] << 10) ^ (src[i + 1] << 5) ^ src[i + 2]) & ((1u << HB) - 1); };
+  size_t i = 0;
+  while (i < n) {
+    int best_len = 0; size_t best_dist = 0;
+    if (i + 3 <= n) {
+      const uint32_t h = hash(i);
+      int32_t c = head[h]; int chain = 16;
+      while (c >= 0 && chain-- && i - (size_t)c <= 32768) {
+        int l = 0; const int maxl = (int)std::min<size_t>(258, n - i);
+        while (l < maxl && src[c + l] == src[i + l]) ++l;
+        if (l > best_len) { best_len = l; best_dist = i - (size_t)c; if (l == maxl) break; }
+        c = prev[c];
+      }
+    }
+    const size_t step = best_len >= 3 ? (size_t)best_len : 1;
+    if (best_len >= 3) {
+      int li = 28; while (kLenBase[li] > best_len) --li;
+      put_litlen(bw, 257 + li); bw.put((uint32_t)(best_len - kLenBase[li]), kLenExtra[li]);
+      int di = 29; while (kDistBase[di] > best_dist) --di;
+      bw.put_rev((uint32_t)di, 5); bw.put((uint32_t)(best_dist - kDistBase[di]), kDistExtra[di]);
+    } else put_litlen(bw, src[i]);
+    for (size_t k = 0; k < step; ++k, ++i) if (i + 3 <= n) { const uint32_t h = hash(i); prev[i] = head[h]; head[h] = (int32_t)i; }
+  }
+  put_litlen(bw, 256);
+  bw.flush();
+  uint32_t a = 1, b = 0;
+  for (size_t k = 0; k < n; ++k) { a = (a + src[k]) % 65521u; b = (b + a) % 65521u; }
+  const uint32_t ad = (b << 16) | a;
+  out.push_back((uint8_t)(ad >> 24)); out.push_back((uint8_t)(ad >> 16)); out.push_back((uint8_t)(ad >> 8)); out.push_back((uint8_t)ad);
+}
+
+// ------------------------------------------------------------------------------ container
+struct scn_sens_frame {
+  float cam2world[16];
+  uint64_t ts_color = 0, ts_depth = 0;
+  std::vector<uint8_t> color, depth;          // compressed payloads as stored in the file
+};
+struct scn_sens {
+  uint32_t version = 4;
+  std::string sensor_name = "Unknown";
+  float color_intr[16], color_extr[16], depth_intr[16], depth_extr[16];
+  int32_t color_comp = -1, depth_comp = -1;
+  uint32_t cw = 0, ch = 0, dw = 0, dh = 0;
+  float depth_shift = 1000.0f;
+  std::vector<scn_sens_frame> frames;
+  std::vector<std::vector<uint8_t>> imu;      // 128-byte records (sensorData.h:786-833), kept verbatim
+};
+
+namespace {
+void identity16(float* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
+template <typename T> bool rd(std::istream& in, T& v) { in.read((char*)&v, sizeof(T)); return (bool)in; }
+const uint64_t kMaxPayload = 1ull << 31;
+}  // namespace
+
+extern "C" {
+
+int scn_sens_open(const char* path, scn_sens** out) {
+  if (!path || !out) return scn::fail(SCN_ERR_ARG, "null argument");
+  std::ifstream in(path, std::ios::binary);
+  if (!in.is_open()) return scn::fail(SCN_ERR_IO, "could not open file %s", path);         // sensorData.h:1253-1255
+  scn_sens* s = new scn_sens();
+  auto bail = [&](int code, const char* msg) { delete s; return scn::fail(code, "%s: %s", path, msg); };
+  if (!rd(in, s->version)) return bail(SCN_ERR_FORMAT, "truncated header");
+  if (s->version != 4) {                                                                     // :882-886
+    const uint32_t v = s->version; delete s;
+    return scn::fail(SCN_ERR_FORMAT, "Invalid file version -- found %u but expectd 4", v);
+  }
+  uint64_t slen = 0;
+  if (!rd(in, slen) || slen > (1u << 20)) return bail(SCN_ERR_FORMAT, "bad sensor name length");
+  s->sensor_name.resize(slen);
+  in.read(&s->sensor_name[0], (std::streamsize)slen);
+  in.read((char*)s->color_intr, 64); in.read((char*)s->color_extr, 64);
+  in.read((char*)s->depth_intr, 64); in.read((char*)s->depth_extr, 64);
+  rd(in, s->color_comp); rd(in, s->depth_comp);
+  rd(in, s->cw); rd(in, s->ch); rd(in, s->dw); rd(in, s->dh); rd(in, s->depth_shift);
+  uint64_t nf = 0;
+  if (!rd(in, nf)) return bail(SCN_ERR_FORMAT, "truncated header");
+  if (nf > (1ull << 32)) return bail(SCN_ERR_FORMAT, "implausible frame count");
+  s->frames.resize(nf);
+  for (uint64_t i = 0; i < nf; ++i) {
+    scn_sens_frame& f = s->frames[i];
+    uint64_t cb = 0, db = 0;
+    in.read((char*)f.cam2world, 64);
+    if (!rd(in, f.ts_color) || !rd(in, f.ts_depth) || !rd(in, cb) || !rd(in, db)) return bail(SCN_ERR_FORMAT, "truncated frame header");
+    if (cb > kMaxPayload || db > kMaxPayload) return bail(SCN_ERR_FORMAT, "implausible payload size");
+    f.color.resize(cb); f.depth.resize(db);
+    if (cb) in.read((char*)f.color.data(), (std::streamsize)cb);
+    if (db) in.read((char*)f.depth.data(), (std::streamsize)db);
+    if (!in) return bail(SCN_ERR_FORMAT, "truncated frame payload");
+  }
+  uint64_t ni = 0;
+  if (rd(in, ni) && ni > 0 && ni < (1ull << 32)) {
+    s->imu.resize(ni);
+    for (uint64_t i = 0; i < ni; ++i) { s->imu[i].resize(128); in.read((char*)s->imu[i].data(), 128); if (!in) return bail(SCN_ERR_FORMAT, "truncated IMU frames"); }
+  }
+  *out = s;
+  return SCN_OK;
+}
+
+void scn_sens_close(scn_sens* s) { delete s; }
+
+int scn_sens_info(const scn_sens* s, scn_sens_info_t* info) {
+  if (!s || !info) return scn::fail(SCN_ERR_ARG, "null argument");
+  memset(info, 0, sizeof(*info));
+  info->version = s->version;
+  info->color_width = s->cw; info->color_height = s->ch; info->depth_width = s->dw; info->depth_height = s->dh;
+  info->color_compression = s->color_comp; info->depth_compression = s->depth_comp;
+  info->depth_shift = s->depth_shift; info->n_frames = s->frames.size(); info->n_imu_frames = s->imu.size();
+  memcpy(info->color_intrinsic, s->color_intr, 64); memcpy(info->color_extrinsic, s->color_extr, 64);
+  memcpy(info->depth_intrinsic, s->depth_intr, 64); memcpy(info->depth_extrinsic, s->depth_extr, 64);
+  snprintf(info->sensor_name, sizeof(info->sensor_name), "%s", s->sensor_name.c_str());
+  return SCN_OK;
+}
+
+int scn_sens_frame_meta(const scn_sens* s, uint64_t i, float cam2world[16], uint64_t* tc, uint64_t* td, uint64_t* cb, uint64_t* db) {
+  if (!s) return scn::fail(SCN_ERR_ARG, "null handle");
+  if (i >= s->frames.size()) return scn::fail(SCN_ERR_ARG, "out of bounds");               // sensorData.h:944
+  const scn_sens_frame& f = s->frames[i];
+  if (cam2world) memcpy(cam2world, f.cam2world, 64);
+  if (tc) *tc = f.ts_color; if (td) *td = f.ts_depth; if (cb) *cb = f.color.size(); if (db) *db = f.depth.size();
+  return SCN_OK;
+}
+
+int scn_sens_frame_depth_u16(const scn_sens* s, uint64_t i, uint16_t* out) {
+  if (!s || !out) return scn::fail(SCN_ERR_ARG, "null argument");
+  if (i >= s->frames.size()) return scn::fail(SCN_ERR_ARG, "out of bounds");
+  const scn_sens_frame& f = s->frames[i];
+  const size_t want = (size_t)s->dw * s->dh * 2;
+  if (s->depth_comp == 0) {                                                                  // TYPE_RAW_USHORT :724-730
+    if (f.depth.empty()) return scn::fail(SCN_ERR_FORMAT, "invalid data");
+    memcpy(out, f.depth.data(), std::min(want, f.depth.size()));
+    return SCN_OK;
+  }
+  if (s->depth_comp == 1) {                                                                  // TYPE_ZLIB_USHORT :703-709
+    std::vector<uint8_t> raw;
+    if (scn::zlib_inflate(f.depth.data(), f.depth.size(), raw, want)) return scn::fail(SCN_ERR_FORMAT, "frame %llu: corrupt zlib depth stream", (unsigned long long)i);
+    if (raw.size() < want) return scn::fail(SCN_ERR_FORMAT, "frame %llu: depth stream holds %zu bytes, need %zu", (unsigned long long)i, raw.size(), want);
+    memcpy(out, raw.data(), want);
+    return SCN_OK;
+  }
+  if (s->depth_comp == 2) return scn::fail(SCN_ERR_UNSUPPORTED, "need UPLINK_COMPRESSION");  // :711-722
+  return scn::fail(SCN_ERR_FORMAT, "invalid type");
+}
+
+int scn_sens_frame_color_rgb8(const scn_sens* s, uint64_t i, uint8_t* out) {
+  if (!s || !out) return scn::fail(SCN_ERR_ARG, "null argument");
+  if (i >= s->frames.size()) return scn::fail(SCN_ERR_ARG, "out of bounds");
+  const scn_sens_frame& f = s->frames[i];
+  const size_t want = (size_t)s->cw * s->ch * 3;
+  if (f.color.empty()) return scn::fail(SCN_ERR_FORMAT, "decompression error");
+  if (s->color_comp == 0) { memcpy(out, f.color.data(), std::min(want, f.color.size())); return SCN_OK; }   // :638-645
+  if (s->color_comp == 2) return scn::jpeg_decode_rgb8(f.color.data(), f.color.size(), s->cw, s->ch, out);
+  if (s->color_comp == 1) return scn::png_decode_rgb8(f.color.data(), f.color.size(), s->cw, s->ch, out);
+  return scn::fail(SCN_ERR_FORMAT, "invliad type");
+}
+
+int scn_sens_frame_payload(const scn_sens* s, uint64_t i, const uint8_t** color, const uint8_t** depth) {
+  if (!s) return scn::fail(SCN_ERR_ARG, "null handle");
+  if (i >= s->frames.size()) return scn::fail(SCN_ERR_ARG, "out of bounds");
+  if (color) *color = s->frames[i].color.data();
+  if (depth) *depth = s->frames[i].depth.data();
+  return SCN_OK;
+}
+
+int scn_sens_set_pose(scn_sens* s, uint64_t i, const float cam2world[16]) {
+  if (!s || !cam2world) return scn::fail(SCN_ERR_ARG, "null argument");
+  if (i >= s->frames.size()) return scn::fail(SCN_ERR_ARG, "out of bounds");
+  memcpy(s->frames[i].cam2world, cam2world, 64);
+  return SCN_OK;
+}
+
+int scn_sens_save(const scn_sens* s, const char* path) {
+  if (!s || !path) return scn::fail(SCN_ERR_ARG, "null argument");
+  std::ofstream out(path, std::ios::binary);
+  if (!out) return scn::fail(SCN_ERR_IO, "Unable to open file for writing: %s", path);       // sensorData.h:1103-1105
+  out.write((const char*)&s->version, 4);
+  const uint64_t slen = s->sensor_name.size();
+  out.write((const char*)&slen, 8); out.write(s->sensor_name.data(), (std::streamsize)slen);
+  out.write((const char*)s->color_intr, 64); out.write((const char*)s->color_extr, 64);
+  out.write((const char*)s->depth_intr, 64); out.write((const char*)s->depth_extr, 64);
+  out.write((const char*)&s->color_comp, 4); out.write((const char*)&s->depth_comp, 4);
+  out.write((const char*)&s->cw, 4); out.write((const char*)&s->ch, 4); out.write((const char*)&s->dw, 4); out.write((const char*)&s->dh, 4);
+  out.write((const char*)&s->depth_shift, 4);
+  const uint64_t nf = s->frames.size();
+  out.write((const char*)&nf, 8);
+  for (const scn_sens_frame& f : s->frames) {
+    const uint64_t cb = f.color.size(), db = f.depth.size();
+    out.write((const char*)f.cam2world, 64);
+    out.write((const char*)&f.ts_color, 8); out.write((const char*)&f.ts_depth, 8);
+    out.write((const char*)&cb, 8); out.write((const char*)&db, 8);
+    out.write((const char*)f.color.data(), (std::streamsize)cb); out.write((const char*)f.depth.data(), (std::streamsize)db);
+  }
+  const uint64_t ni = s->imu.size();
+  out.write((const char*)&ni, 8);
+  for (const auto& r : s->imu) out.write((const char*)r.data(), 128);
+  return out ? SCN_OK : scn::fail(SCN_ERR_IO, "write failed: %s", path);
+}
+
+int scn_sens_create(uint32_t cw, uint32_t ch, uint32_t dw, uint32_t dh, const float color_intr[16], const float depth_intr[16],
+                    int32_t color_comp, int32_t depth_comp, float depth_shift, const char* name, scn_sens** out) {
+  if (!out) return scn::fail(SCN_ERR_ARG, "null argument");
+  if (color_comp < 0 || color_comp > 2 || depth_comp < 0 || depth_comp > 1) return scn::fail(SCN_ERR_UNSUPPORTED, "unknown compression type");
+  scn_sens* s = new scn_sens();
+  s->cw = cw; s->ch = ch; s->dw = dw; s->dh = dh; s->color_comp = color_comp; s->depth_comp = depth_comp;
+  s->depth_shift = depth_shift; s->sensor_name = name ? name : "Unknown";
+  identity16(s->color_extr); identity16(s->depth_extr); identity16(s->color_intr); identity16(s->depth_intr);
+  if (color_intr) memcpy(s->color_intr, color_intr, 64);
+  if (depth_intr) memcpy(s->depth_intr, depth_intr, 64);
+  *out = s;
+  return SCN_OK;
+}
+
+int scn_sens_add_frame(scn_sens* s, const uint8_t* color, uint64_t color_bytes, const uint16_t* depth, const float cam2world[16],
+                       uint64_t ts_color, uint64_t ts_depth) {
+  if (!s) return scn::fail(SCN_ERR_ARG, "null handle");
+  scn_sens_frame f;
+  if (cam2world) memcpy(f.cam2world, cam2world, 64); else identity16(f.cam2world);
+  f.ts_color = ts_color; f.ts_depth = ts_depth;
+  if (color) {
+    if (s->color_comp == 0) color_bytes = (uint64_t)s->cw * s->ch * 3;
+    f.color.assign(color, color + color_bytes);
+  }
+  if (depth) {
+    const size_t raw = (size_t)s->dw * s->dh * 2;
+    if (s->depth_comp == 0) f.depth.assign((const uint8_t*)depth, (const uint8_t*)depth + raw);
+    else scn::zlib_deflate((const uint8_t*)depth, raw, f.depth);
+  }
+  s->frames.push_back(std::move(f));
+  return SCN_OK;
+}
+
+// operator<< (sensorData.h:1941-1955)
+int64_t scn_sens_describe(const scn_sens* s, char* buf, uint64_t cap) {
+  if (!s) return scn::fail(SCN_ERR_ARG, "null handle");
+  std::ostringstream o;
+  o << "CalibratedSensorData:\n";
+  o << '\t' << "sensorData.m_versionNumber" << '=' << s->version << '\n';
+  o << '\t' << "sensorData.m_sensorName" << '=' << s->sensor_name << '\n';
+  o << '\t' << "sensorData.m_colorWidth" << '=' << s->cw << '\n';
+  o << '\t' << "sensorData.m_colorHeight" << '=' << s->ch << '\n';
+  o << '\t' << "sensorData.m_depthWidth" << '=' << s->dw << '\n';
+  o << '\t' << "sensorData.m_depthHeight" << '=' << s->dh << '\n';
+  o << '\t' << "sensorData.m_depthShift" << '=' << s->depth_shift << '\n';
+  o << '\t' << "sensorData.m_frames.size()" << '=' << s->frames.size() << '\n';
+  o << '\t' << "sensorData.m_IMUFrames.size()" << '=' << s->imu.size() << '\n';
+  const std::string t = o.str();
+  if (buf && cap) { const size_t n = std::min<size_t>(cap - 1, t.size()); memcpy(buf, t.data(), n); buf[n] = 0; }
+  return (int64_t)t.size();
+}
+
+namespace {
+std::string counter_name(const std::string& base, unsigned cur, const std::string& ending, unsigned digits) {   // StringCounter :1292-1339
+  std::stringstream ss;
+  ss << base;
+  for (unsigned i = std::max(1u, (unsigned)ceilf(log10f((float)cur + 1))); i < digits; i++) ss << "0";
+  ss << cur;
+  ss << (ending[0] == '.' ? ending : "." + ending);
+  return ss.str();
+}
+}  // namespace
+
+int scn_sens_save_to_images(const scn_sens* s, const char* out_dir) {
+  if (!s || !out_dir) return scn::fail(SCN_ERR_ARG, "null argument");
+  const std::string folder = out_dir;
+  struct stat sb;
+  if (stat(folder.c_str(), &sb) != 0) mkdir(folder.c_str(), 0777);
+  {
+    std::ofstream m(folder + "/" + "_info.txt");
+    if (!m) return scn::fail(SCN_ERR_IO, "cannot open file %s/_info.txt", out_dir);
+    m << "m_versionNumber" << " = " << s->version << '\n';
+    m << "m_sensorName" << " = " << s->sensor_name << '\n';
+    m << "m_colorWidth" << " = " << s->cw << '\n';
+    m << "m_colorHeight" << " = " << s->ch << '\n';
+    m << "m_depthWidth" << " = " << s->dw << '\n';
+    m << "m_depthHeight" << " = " << s->dh << '\n';
+    m << "m_depthShift" << " = " << s->depth_shift << '\n';
+    const char* names[4] = {"m_calibrationColorIntrinsic", "m_calibrationColorExtrinsic", "m_calibrationDepthIntrinsic", "m_calibrationDepthExtrinsic"};
+    const float* mats[4] = {s->color_intr, s->color_extr, s->depth_intr, s->depth_extr};
+    for (int k = 0; k < 4; ++k) { m << names[k] << " = "; for (int i = 0; i < 16; ++i) m << mats[k][i] << " "; m << "\n"; }
+    m << "m_frames.size" << " = " << (uint64_t)s->frames.size() << "\n";
+    if (!s->imu.empty()) std::cout << "warning sensor has imu frames; but writing is not implemented here" << std::endl;
+  }
+  if (s->frames.empty()) return SCN_OK;
+  const std::string cend = s->color_comp == 2 ? "jpg" : "png";
+  std::cout << std::endl;
+  std::vector<uint16_t> depth((size_t)s->dw * s->dh);
+  for (size_t i = 0; i < s->frames.size(); ++i) {
+    std::cout << "\r[ processing frame " << std::to_string(i) << " of " << std::to_string(s->frames.size()) << " ]";
+    const scn_sens_frame& f = s->frames[i];
+    const std::string base = folder + "/" + "frame-";
+    if (s->color_comp == 1 || s->color_comp == 2) {
+      const std::string cf = counter_name(base, (unsigned)i, "color." + cend, 6);
+      FILE* fp = fopen(cf.c_str(), "wb");
+      if (!fp) return scn::fail(SCN_ERR_IO, "cannot open file %s", cf.c_str());
+      fwrite(f.color.data(), 1, f.color.size(), fp); fclose(fp);
+    } else if (s->color_comp == 0) {
+      // the reference re-encodes raw colour as PNG through stb_image_write (:1417-1425); we write the
+      // same pixels as a binary PPM next to it instead (documented deviation)
+      const std::string cf = counter_name(base, (unsigned)i, "color.ppm", 6);
+      FILE* fp = fopen(cf.c_str(), "wb");
+      if (!fp) return scn::fail(SCN_ERR_IO, "cannot open file %s", cf.c_str());
+      fprintf(fp, "P6\n%u %u\n255\n", s->cw, s->ch); fwrite(f.color.data(), 1, f.color.size(), fp); fclose(fp);
+    } else return scn::fail(SCN_ERR_FORMAT, "unknown format");
+    int rc = scn_sens_frame_depth_u16(s, i, depth.data());
+    if (rc) return rc;
+    {                                                                                        // saveAsPGM :1342-1375
+      std::ofstream of(counter_name(base, (unsigned)i, "depth.pgm", 6), std::ios::binary);
+      std::stringstream ss;
+      ss << "P5\n";
+      ss << "# data values are 16-bit each; depth shift is " << s->depth_shift << "\n";
+      ss << s->dw << " " << s->dh << "\n";
+      ss << std::numeric_limits<unsigned short>::max() << "\n";
+      of << ss.str();
+      uint8_t* dc = (uint8_t*)depth.data();
+      for (size_t k = 0; k < depth.size(); ++k) std::swap(dc[2 * k], dc[2 * k + 1]);
+      of.write((const char*)depth.data(), (std::streamsize)(depth.size() * 2));
+    }
+    {                                                                                        // savePoseFile :1706-1714
+      std::ofstream pf(counter_name(base, (unsigned)i, ".pose.txt", 6));
+      const float* m = f.cam2world;
+      pf << m[0] << " " << m[1] << " " << m[2] << " " << m[3] << "\n" << m[4] << " " << m[5] << " " << m[6] << " " << m[7] << "\n"
+         << m[8] << " " << m[9] << " " << m[10] << " " << m[11] << "\n" << m[12] << " " << m[13] << " " << m[14] << " " << m[15];
+    }
+  }
+  return SCN_OK;
+}
+
+// `sens <file.sens> [outDir]` (SensReader/c++/src/main.cpp:28-97)
+int scn_sens_main(int argc, const char** argv) {
+  std::string filename = "scene0001_00.sens", outDir = "./out/";
+  if (argc >= 2) filename = argv[1];
+  else { std::cout << "run ./sens <sensfilename>.sens"; std::cout << "type in filename manually: "; std::cin >> filename; }
+  if (argc >= 3) outDir = argv[2];
+  std::cout << "filename =\t" << filename << std::endl;
+  std::cout << "outDir =\t" << outDir << std::endl;
+  std::cout << "loading from file... ";
+  scn_sens* s = nullptr;
+  if (scn_sens_open(filename.c_str(), &s)) { std::cout << "Exception caught! " << scn_last_error() << std::endl; return EXIT_FAILURE; }
+  std::cout << "done!" << std::endl;
+  std::vector<char> buf(4096);
+  scn_sens_describe(s, buf.data(), buf.size());
+  std::cout << buf.data() << std::endl;
+  if (scn_sens_save_to_images(s, outDir.c_str())) { std::cout << "Exception caught! " << scn_last_error() << std::endl; scn_sens_close(s); return EXIT_FAILURE; }
+  if (!s->frames.empty()) {                         // processFrame(sd, 0): decode one frame of each stream (main.cpp:6-26,64)
+    std::vector<uint16_t> d((size_t)s->dw * s->dh); std::vector<uint8_t> c((size_t)s->cw * s->ch * 3);
+    scn_sens_frame_depth_u16(s, 0, d.data());
+    scn_sens_frame_color_rgb8(s, 0, c.data());
+  }
+  std::cout << std::endl;
+  std::cout << "All done :)" << std::endl;
+  scn_sens_close(s);
+  return 0;
+}
+
+}  // extern "C"

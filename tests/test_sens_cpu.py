@@ -1,0 +1,148 @@
+"""SensReader host logic (no GPU): `.sens` v4 container, depth/colour decode, writer, saveToImages —
+byte-exact against the UNMODIFIED reference ml::SensorData (oracle/_ref/libref_sens.so, sens_ref)."""
+import ctypes as C
+import filecmp
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from scannet_b200 import synth
+from scannet_b200.sens import SensFile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_sens.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sens_ref")
+need_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def ref_lib():
+    L = C.CDLL(REF_SO)
+    L.ref_sens_open.restype = C.c_void_p; L.ref_sens_open.argtypes = [C.c_char_p]
+    L.ref_sens_close.argtypes = [C.c_void_p]
+    L.ref_sens_info.argtypes = [C.c_void_p] * 7
+    L.ref_sens_frame_meta.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
+    L.ref_sens_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ref_sens_color.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    return L
+
+
+def jpeg_bytes(rgb, quality=85, subsample=None):
+    import cv2
+    params = [int(cv2.IMWRITE_JPEG_QUALITY), quality]
+    if subsample is not None:
+        params += [int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR), subsample]
+    ok, buf = cv2.imencode(".jpg", rgb[:, :, ::-1], params)
+    assert ok
+    return buf.tobytes()
+
+
+@pytest.fixture(scope="module")
+def stream(tmp_path_factory, built):
+    d = tmp_path_factory.mktemp("sens")
+    D, Cc, P, K = synth.make_frames(5, seed=2, width=160, height=120, loop_frames=50, noise_mm=2.0, drop=0.05, invalid_pose_every=4)
+    rng = np.random.default_rng(0)
+    Cc = np.clip(Cc.astype(np.int32) + rng.integers(-20, 20, Cc.shape), 0, 255).astype(np.uint8)   # texture for the JPEG path
+    p = str(d / "synth.sens")
+    synth.write_sens(p, D, Cc, P, K, depth_comp=1, color_comp=2, jpeg_encoder=jpeg_bytes)
+    return p, D, Cc, P, K
+
+
+@need_ref
+def test_header_and_frames_match_reference(stream):
+    p, D, Cc, P, K = stream
+    s = SensFile(p); L = ref_lib(); r = L.ref_sens_open(p.encode())
+    assert r
+    dims = (C.c_uint32 * 4)(); ds = C.c_float(); comp = (C.c_int32 * 2)(); nf = C.c_uint64(); ni = C.c_uint64(); mats = (C.c_float * 64)()
+    L.ref_sens_info(r, dims, C.byref(ds), comp, C.byref(nf), C.byref(ni), mats)
+    i = s.info
+    assert list(dims) == [i.color_width, i.color_height, i.depth_width, i.depth_height]
+    assert ds.value == i.depth_shift and list(comp) == [i.color_compression, i.depth_compression] and nf.value == i.n_frames == 5
+    assert list(mats) == list(i.color_intrinsic) + list(i.color_extrinsic) + list(i.depth_intrinsic) + list(i.depth_extrinsic)
+    for f in range(5):
+        T = np.zeros(16, np.float32); a = C.c_uint64(); b = C.c_uint64(); c = C.c_uint64(); d = C.c_uint64()
+        L.ref_sens_frame_meta(r, f, T.ctypes.data, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        T2, tc, td, cb, db = s.frame_meta(f)
+        assert T.tobytes() == T2.tobytes() and (a.value, b.value, c.value, d.value) == (tc, td, cb, db)
+        rd = np.zeros((120, 160), np.uint16); assert L.ref_sens_depth(r, f, rd.ctypes.data) == 0
+        assert (s.depth(f) == rd).all() and (rd == D[f]).all()
+        rc = np.zeros((120, 160, 3), np.uint8); assert L.ref_sens_color(r, f, rc.ctypes.data) == 0
+        assert (s.color(f) == rc).all(), "JPEG decode differs from the reference (stb_image) bytes"
+    L.ref_sens_close(r); s.close()
+
+
+@need_ref
+@pytest.mark.parametrize("sub,wh", [(0x111111, (67, 45)), (0x211111, (66, 47)), (0x221111, (70, 33)), (0x121111, (64, 48)), (0x411111, (72, 40))])
+def test_jpeg_subsampling_modes_match_stb(tmp_path, built, sub, wh):
+    """4:4:4, 4:2:2, 4:2:0, 4:4:0, 4:1:1 chroma layouts at non-MCU-aligned sizes."""
+    W, H = wh
+    rng = np.random.default_rng(sub)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 5 + yy) % 256, (yy * 7) % 256, (xx * yy) % 256], -1).astype(np.uint8)
+    img = np.clip(img.astype(int) + rng.integers(-30, 30, img.shape), 0, 255).astype(np.uint8)
+    D = np.full((1, 8, 8), 1000, np.uint16); P = np.eye(4, dtype=np.float32)[None]
+    p = str(tmp_path / "j.sens")
+    synth.write_sens(p, D, img[None], P, np.eye(4, dtype=np.float32), depth_comp=0, color_comp=2,
+                     jpeg_encoder=lambda x: jpeg_bytes(x, 70, sub))
+    L = ref_lib(); r = L.ref_sens_open(p.encode()); s = SensFile(p)
+    rc = np.zeros((H, W, 3), np.uint8); assert L.ref_sens_color(r, 0, rc.ctypes.data) == 0
+    assert (s.color(0) == rc).all()
+    L.ref_sens_close(r)
+
+
+@need_ref
+def test_writer_round_trip_through_reference(tmp_path, built):
+    """scn_sens_create/add_frame/save -> the reference loads it and decodes identical depth (our deflate, its inflate)."""
+    D, Cc, P, K = synth.make_frames(3, seed=4, width=96, height=64, loop_frames=30, noise_mm=1.0)
+    w = SensFile.create((96, 64), (96, 64), K, K, color_compression=0, depth_compression=1)
+    for f in range(3):
+        w.add_frame(Cc[f], D[f], P[f], f * 33333, f * 33333)
+    p = str(tmp_path / "ours.sens"); w.save(p)
+    L = ref_lib(); r = L.ref_sens_open(p.encode()); assert r
+    for f in range(3):
+        rd = np.zeros((64, 96), np.uint16); assert L.ref_sens_depth(r, f, rd.ctypes.data) == 0
+        assert (rd == D[f]).all()
+        rc = np.zeros((64, 96, 3), np.uint8); assert L.ref_sens_color(r, f, rc.ctypes.data) == 0
+        assert (rc == Cc[f]).all()
+    L.ref_sens_close(r)
+    s = SensFile(p)
+    assert s.n_frames == 3 and (s.depth(1) == D[1]).all() and (s.color(2) == Cc[2]).all()
+    # compression actually compresses
+    assert s.frame_meta(0)[4] < 96 * 64 * 2 * 0.8
+    # pose write-back + byte-identical re-save
+    T = np.eye(4, dtype=np.float32); T[0, 3] = 1.5
+    s.set_pose(1, T); p2 = str(tmp_path / "ours2.sens"); s.save(p2)
+    s2 = SensFile(p2); assert (s2.pose(1) == T).all() and (s2.depth(2) == D[2]).all()
+
+
+@need_ref
+def test_cli_outputs_match_reference_binary(stream, tmp_path):
+    """`sens <file> <outDir>`: identical _info.txt, .pose.txt, .depth.pgm, .color.jpg files and header text."""
+    p = stream[0]
+    ours = tmp_path / "ours"; ref = tmp_path / "ref"
+    tool = os.path.join(ROOT, "scannet_b200", "bin", "sens")
+    o1 = subprocess.run([tool, p, str(ours)], capture_output=True, text=True)
+    o2 = subprocess.run([REF_BIN, p, str(ref)], capture_output=True, text=True)
+    assert o1.returncode == 0 and o2.returncode == 0
+    assert o1.stdout.replace(str(ours), "X") == o2.stdout.replace(str(ref), "X")
+    names = sorted(os.listdir(ref))
+    assert names == sorted(os.listdir(ours)) and len(names) == 1 + 3 * 5
+    match, mismatch, err = filecmp.cmpfiles(ours, ref, names, shallow=False)
+    assert not mismatch and not err, (mismatch, err)
+
+
+def test_errors_are_statuses_not_crashes(tmp_path, built):
+    from scannet_b200 import ScnError
+    with pytest.raises(ScnError):
+        SensFile(str(tmp_path / "missing.sens"))
+    bad = tmp_path / "bad.sens"; bad.write_bytes(b"\x03\x00\x00\x00" + b"\x00" * 64)
+    with pytest.raises(ScnError) as e:
+        SensFile(str(bad))
+    assert "Invalid file version" in str(e.value)
+    trunc = tmp_path / "trunc.sens"
+    D, Cc, P, K = synth.make_frames(1, seed=1, width=32, height=24)
+    synth.write_sens(str(trunc), D, Cc, P, K, depth_comp=1, color_comp=0)
+    data = trunc.read_bytes(); trunc.write_bytes(data[: len(data) // 2])
+    with pytest.raises(ScnError):
+        SensFile(str(trunc))
