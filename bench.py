@@ -170,6 +170,37 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- Segmentator side benchmark
+def seg_bench(c5: bool):
+    """BASELINE.json configs[0]/[4]: Segmentator on a ~50k-vertex (and optionally 2M-vertex) mesh, GPU path vs the
+    reference CPU code (oracle/_ref built from the unmodified reference when present, else the C restatement)."""
+    import tempfile
+    import oracle_bindings as ob
+    from scannet_b200 import segmentator, synth
+    out = {}
+    for name, (nx, ny) in ([("c1_50k", (250, 200))] + ([("c5_2m", (1600, 1250))] if c5 else [])):
+        xyz, tri = synth.make_feature_mesh(nx, ny, seed=5)
+        segmentator.segment_mesh(xyz[:3000], tri[(tri < 3000).all(1)])            # warm-up (context, allocator)
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter(); seg = segmentator.segment_mesh(xyz, tri); dt = time.perf_counter() - t0
+            ms, launches = segmentator.last_timings(); runs.append((dt, ms, launches))
+        runs.sort(key=lambda r: r[0]); dt, ms, launches = runs[1]
+        t0 = time.perf_counter(); ref = ob.oracle_segment(xyz, tri); t_port = time.perf_counter() - t0
+        rec = {"verts": int(len(xyz)), "faces": int(len(tri)), "segments": int(len(set(seg.tolist()))), "bit_identical_to_cpu": bool((seg == ref).all()),
+               "gpu_path_s": dt, "stages_ms": {k: round(v, 3) for k, v in zip(["h2d", "normals", "weights", "sort", "kruskal_host", "small_merge_host", "gather_d2h_labels", "total"], ms)},
+               "sort_kernel_launches": launches, "cpu_port_s": t_port, "cpu_port_kind": "oracle/seg_oracle.c -O2, 1 thread, arrays in memory"}
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_segmentator.so")
+        if os.path.exists(ref_so):
+            with tempfile.TemporaryDirectory() as d:
+                p = os.path.join(d, "m.ply"); synth.write_ply(p, xyz, tri)
+                t0 = time.perf_counter(); ids = ob.ref_segment_file(p, len(xyz)); rec["cpu_reference_s"] = time.perf_counter() - t0
+                rec["cpu_reference_kind"] = "unmodified reference segment() incl. tinyply load, -O2, 1 thread"
+                rec["bit_identical_to_reference"] = bool((ids == seg).all())
+        out[name] = rec
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -183,25 +214,25 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=40, help="bounded CPU sample (frames)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--color", action="store_true", help="also fuse colour")
+    ap.add_argument("--no-seg", action="store_true", help="skip the Segmentator side benchmark")
+    ap.add_argument("--seg-c5", action="store_true", help="also run the 2M-vertex Segmentator case")
     ap.add_argument("--simple-kernel", action="store_true", help="use the plain 2-voxel/thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
-    import torch.distributed as dist
+    from scannet_b200 import dist as sdist
     from scannet_b200 import tsdf
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = sdist.env_rank()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    grp = sdist.Group("nccl", dev)
 
     S, Wm, F = args.steps, args.warmup, args.frames_per_step
     n_frames = (S + Wm) * F
-    sc, P = scene_poses(n_frames, rank, args.loop)
+    sc, P = scene_poses(n_frames, sdist.scene_seed_for_rank(rank), args.loop)     # one scene per rank / GPU
     K = sc.intrinsics()
     d_depth = render_depth_torch(sc, P, dev)                                   # [N,H,W] int16 (u16 bits), HBM resident
     h_depth = torch.empty(d_depth.shape, dtype=torch.int16, pin_memory=True)
@@ -213,11 +244,7 @@ def main():
                                 flags=flags | (tsdf.KERNEL_SIMPLE if args.simple_kernel else 0))
         return tsdf.TsdfVolume(p, device=local, stream=torch.cuda.current_stream().cuda_stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = grp.barrier
 
     def timed(fn_step):
         """W warm-up steps, then exactly S steps bracketed by barrier+sync, CUDA events on the launch stream."""
@@ -231,10 +258,7 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return grp.reduce_throughput(S * F, ms)       # (frames over all ranks, max ms over ranks)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -256,7 +280,7 @@ def main():
             vol.profile(True); state["prof"] = True
         step_dev(s)
 
-    ms_dev = timed(step_dev_prof)
+    frames_all, ms_dev = timed(step_dev_prof)
     vol.sync()
     st = vol.stats()
     alloc_ms, integ_ms, n_batches, union_blocks = vol.kernel_times()
@@ -273,7 +297,7 @@ def main():
         vol2.integrate_batch_ptr(F, hbase + s * F * frame_bytes, None, P[s * F:(s + 1) * F], K)
         vol2.stats()                                            # D2H read of the step's result (counters)
 
-    ms_e2e = timed(step_e2e)
+    frames_all2, ms_e2e = timed(step_e2e)
     vol2.sync()
     vol2.close()
     clocks = sampler.stop() if sampler else None
@@ -281,8 +305,8 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         frames_timed = S * F
-        value = world * frames_timed / (ms_dev / 1e3)
-        e2e = world * frames_timed / (ms_e2e / 1e3)
+        value = frames_all / (ms_dev / 1e3)
+        e2e = frames_all2 / (ms_e2e / 1e3)
         alg_integrate = 16.0 * nu + 16.0 * nb                     # bytes, k_integrate, timed steps (this rank)
         per_launch_bytes = alg_integrate / max(n_batches, 1)
         per_launch_ms = integ_ms / max(n_batches, 1)
@@ -315,10 +339,13 @@ def main():
         }
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_arm(args)
+        if world == 1 and not args.no_seg:
+            try:
+                line["segmentator"] = seg_bench(args.seg_c5)
+            except Exception as e:          # the side benchmark must never take the headline line down
+                line["segmentator"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    grp.close()
 
 
 if __name__ == "__main__":

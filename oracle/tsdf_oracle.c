@@ -283,3 +283,142 @@ void oracle_tsdf_export(const oracle_tsdf* o, int32_t* block_xyz, void* voxels) 
   }
   free(ki);
 }
+
+/* ------------------------------------------------------------------ marching cubes -----
+ * Own spec (the reference's meshing lives in the external binaries).  Independent statement of the rules
+ * the product implements in csrc/mc.cu: usable voxels, valid cubes, lattice-edge vertices, a 256-case
+ * table built by face-contour linking, deterministic ordering, dropped unreferenced vertices. */
+static const ovoxel* vox_at(const oracle_tsdf* o, int gx, int gy, int gz) {
+  const int bx = gx >> 3, by = gy >> 3, bz = gz >> 3;                 /* arithmetic shift = floor division by 8 */
+  if (!key_ok(bx, by, bz)) return NULL;
+  const uint64_t key = pack_key(bx, by, bz);
+  uint64_t s = mix64(key) & (o->cap - 1);
+  while (o->keys[s] != EMPTY_KEY && o->keys[s] != key) s = (s + 1) & (o->cap - 1);
+  if (o->keys[s] != key) return NULL;
+  return o->vox + (size_t)o->vals[s] * 512 + ((gx & 7) | ((gy & 7) << 3) | ((gz & 7) << 6));
+}
+static int vox_usable(const ovoxel* v, float thr) { return v && v->w > 0 && fabsf(v->sdf) <= thr; }
+
+static int edge_of(int c0, int c1) {                                   /* edge id = axis*4 + (u | v<<1) */
+  const int d = c0 ^ c1, a = d == 1 ? 0 : (d == 2 ? 1 : 2), lo = c0 & ~d;
+  const int c[3] = { lo & 1, (lo >> 1) & 1, (lo >> 2) & 1 };
+  const int u = c[a == 0 ? 1 : 0], v = c[a == 2 ? 1 : 2];
+  return a * 4 + (u | (v << 1));
+}
+static void make_case(int cs, int* ntri, int tri[36]) {
+  int next[12], seen[12], nt = 0;
+  for (int i = 0; i < 12; ++i) { next[i] = -1; seen[i] = 0; }
+  for (int a = 0; a < 3; ++a) for (int s = 0; s < 2; ++s) {
+    const int b = (a + 1) % 3, c = (a + 2) % 3;
+    int p[4];
+    /* face corners counter-clockwise seen from outside the cube */
+    const int vb[2][4] = { {0, 0, 1, 1}, {0, 1, 1, 0} }, vc[2][4] = { {0, 1, 1, 0}, {0, 0, 1, 1} };
+    for (int k = 0; k < 4; ++k) { int off[3]; off[a] = s; off[b] = vb[s][k]; off[c] = vc[s][k]; p[k] = off[0] | (off[1] << 1) | (off[2] << 2); }
+    for (int k = 0; k < 4; ++k) {
+      const int prev = (k + 3) & 3;
+      if (((cs >> p[prev]) & 1) || !((cs >> p[k]) & 1)) continue;       /* k starts a run of inside corners */
+      int m = k;
+      while ((cs >> p[(m + 1) & 3]) & 1) m = (m + 1) & 3;
+      next[edge_of(p[prev], p[k])] = edge_of(p[m], p[(m + 1) & 3]);     /* entering edge -> leaving edge */
+    }
+  }
+  for (int e0 = 0; e0 < 12; ++e0) {
+    if (next[e0] < 0 || seen[e0]) continue;
+    int loop[12], n = 0;
+    for (int e = e0; !seen[e]; e = next[e]) { seen[e] = 1; loop[n++] = e; }
+    for (int i = 1; i + 1 < n; ++i) { tri[3 * nt] = loop[0]; tri[3 * nt + 1] = loop[i]; tri[3 * nt + 2] = loop[i + 1]; ++nt; }
+  }
+  *ntri = nt;
+}
+
+void oracle_mc_table(uint8_t* ntri_out /*256*/, uint8_t* tri_out /*256*36*/) {
+  for (int cs = 0; cs < 256; ++cs) {
+    int nt, tri[36];
+    make_case(cs, &nt, tri);
+    ntri_out[cs] = (uint8_t)nt;
+    for (int i = 0; i < 36; ++i) tri_out[cs * 36 + i] = (uint8_t)(i < 3 * nt ? tri[i] : 0);
+  }
+}
+
+/* Returns malloc'ed arrays (free with oracle_free). */
+void oracle_tsdf_extract_mesh(const oracle_tsdf* o, float thresh_factor, float** xyz_out, uint8_t** rgb_out,
+                              uint32_t** tri_out, uint64_t* nv_out, uint64_t* nf_out) {
+  const uint64_t n = o->n_blocks;
+  const float vs = o->p.voxel_size;
+  const float thr = thresh_factor * vs;
+  uint64_t* ki = (uint64_t*)malloc((n ? n : 1) * 16);
+  for (uint64_t i = 0; i < n; ++i) { ki[2 * i] = o->block_key[i]; ki[2 * i + 1] = i; }
+  qsort(ki, n, 16, cmp_u64idx);
+  /* rank of each heap index in key order */
+  uint32_t* rank = (uint32_t*)malloc((n ? n : 1) * 4);
+  for (uint64_t j = 0; j < n; ++j) rank[ki[2 * j + 1]] = (uint32_t)j;
+  int64_t* vid = (int64_t*)malloc((n ? n : 1) * 512 * 3 * sizeof(int64_t));
+  size_t capv = 1 << 16, nv = 0;
+  float* pos = (float*)malloc(capv * 12); uint8_t* col = (uint8_t*)malloc(capv * 3);
+  /* vertices */
+  for (uint64_t j = 0; j < n; ++j) {
+    int32_t b[3]; unpack_key(ki[2 * j], b);
+    for (int l = 0; l < 512; ++l) {
+      const int g[3] = { 8 * b[0] + (l & 7), 8 * b[1] + ((l >> 3) & 7), 8 * b[2] + (l >> 6) };
+      const ovoxel* v0 = vox_at(o, g[0], g[1], g[2]);
+      for (int a = 0; a < 3; ++a) {
+        int64_t id = -1;
+        const ovoxel* v1 = vox_at(o, g[0] + (a == 0), g[1] + (a == 1), g[2] + (a == 2));
+        if (vox_usable(v0, thr) && vox_usable(v1, thr) && ((v0->sdf < 0.0f) != (v1->sdf < 0.0f))) {
+          if (nv == capv) { capv *= 2; pos = (float*)realloc(pos, capv * 12); col = (uint8_t*)realloc(col, capv * 3); }
+          const float t = v0->sdf / (v0->sdf - v1->sdf);
+          for (int i = 0; i < 3; ++i) pos[3 * nv + i] = (i == a ? (float)g[i] + t : (float)g[i]) * vs;
+          const uint8_t c0[3] = { v0->r, v0->g, v0->b }, c1[3] = { v1->r, v1->g, v1->b };
+          for (int ch = 0; ch < 3; ++ch)
+            col[3 * nv + ch] = (uint8_t)(int)(fmaf(t, (float)c1[ch] - (float)c0[ch], (float)c0[ch]) + 0.5f);
+          id = (int64_t)nv++;
+        }
+        vid[(j * 512 + l) * 3 + a] = id;
+      }
+    }
+  }
+  /* triangles */
+  size_t capt = 1 << 16, nt = 0;
+  uint32_t* tri = (uint32_t*)malloc(capt * 12);
+  uint8_t* used = (uint8_t*)calloc(nv ? nv : 1, 1);
+  static uint8_t T_n[256], T_t[256 * 36]; oracle_mc_table(T_n, T_t);
+  for (uint64_t j = 0; j < n; ++j) {
+    int32_t b[3]; unpack_key(ki[2 * j], b);
+    for (int l = 0; l < 512; ++l) {
+      const int g[3] = { 8 * b[0] + (l & 7), 8 * b[1] + ((l >> 3) & 7), 8 * b[2] + (l >> 6) };
+      int cs = 0, ok = 1;
+      for (int c = 0; c < 8 && ok; ++c) {
+        const ovoxel* v = vox_at(o, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+        if (!vox_usable(v, thr)) ok = 0; else if (v->sdf < 0.0f) cs |= 1 << c;
+      }
+      if (!ok) continue;
+      for (int k = 0; k < T_n[cs]; ++k) {
+        if (nt == capt) { capt *= 2; tri = (uint32_t*)realloc(tri, capt * 12); }
+        for (int q = 0; q < 3; ++q) {
+          const int e = T_t[cs * 36 + 3 * k + q], a = e >> 2, u = e & 1, v = (e >> 1) & 1;
+          int off[3];
+          if (a == 0) { off[0] = 0; off[1] = u; off[2] = v; } else if (a == 1) { off[0] = u; off[1] = 0; off[2] = v; } else { off[0] = u; off[1] = v; off[2] = 0; }
+          const int h[3] = { g[0] + off[0], g[1] + off[1], g[2] + off[2] };
+          const uint64_t key = pack_key(h[0] >> 3, h[1] >> 3, h[2] >> 3);
+          uint64_t s = mix64(key) & (o->cap - 1);
+          while (o->keys[s] != key) s = (s + 1) & (o->cap - 1);
+          const uint64_t jj = rank[o->vals[s]];
+          const int64_t id = vid[(jj * 512 + ((h[0] & 7) | ((h[1] & 7) << 3) | ((h[2] & 7) << 6))) * 3 + a];
+          tri[3 * nt + q] = (uint32_t)id; used[id] = 1;
+        }
+        ++nt;
+      }
+    }
+  }
+  /* drop unreferenced vertices, keep order */
+  uint32_t* newid = (uint32_t*)malloc((nv ? nv : 1) * 4);
+  size_t nv2 = 0;
+  for (size_t i = 0; i < nv; ++i) if (used[i]) {
+    newid[i] = (uint32_t)nv2;
+    memmove(pos + 3 * nv2, pos + 3 * i, 12); memmove(col + 3 * nv2, col + 3 * i, 3); ++nv2;
+  }
+  for (size_t i = 0; i < 3 * nt; ++i) tri[i] = newid[tri[i]];
+  free(newid); free(used); free(vid); free(rank); free(ki);
+  *xyz_out = pos; *rgb_out = col; *tri_out = tri; *nv_out = nv2; *nf_out = nt;
+}
+void oracle_free(void* p) { free(p); }

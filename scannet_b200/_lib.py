@@ -2,7 +2,7 @@
 
 There is deliberately NO fallback: if libscannet_b200.so is missing the import fails loudly
 with build instructions, and every compute entry point fails with SCN_ERR_CUDA when no B200
-is visible.  Nothing here imports ``oracle/``."""
+is visible.  The test oracles are never loaded from this package."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,0 +1,122 @@
+// `fuse` — the reconstruction stage contract of the reference pipeline in library form:
+//   <exe> <params.txt> [<params2.txt>] <file.sens> [out.ply]        (Server/scan_processor.py:27-35,123-138)
+// Reads the .sens stream (SensReader), fuses every frame that has a valid pose into the hashed TSDF volume
+// (poses come from the file: camera tracking / bundle adjustment is not part of this path), extracts the
+// surface with marching cubes and writes `<base>_vh.ply` in the VCGLIB layout the `segment` stage reads
+// (Server/config/scan_stages.json:33-37).  Host decode (inflate / JPEG) runs on a thread pool one chunk ahead
+// of the GPU; frames are handed over in pinned memory.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "scn_common.h"
+
+namespace {
+
+struct Chunk { uint16_t* depth = nullptr; uint8_t* rgb = nullptr; std::vector<float> poses; uint32_t n = 0; int rc = 0; std::string err; };
+
+// colour pixel for every depth pixel: K_c * K_d^-1 * (x, y, 1), nearest (sensorData.h:1577-1586 with identity extrinsics)
+void build_color_lut(const scn_sens_info_t& in, std::vector<int32_t>& lut) {
+  const uint32_t W = in.depth_width, H = in.depth_height;
+  lut.resize((size_t)W * H);
+  const float fxd = in.depth_intrinsic[0], cxd = in.depth_intrinsic[2], fyd = in.depth_intrinsic[5], cyd = in.depth_intrinsic[6];
+  const float fxc = in.color_intrinsic[0], cxc = in.color_intrinsic[2], fyc = in.color_intrinsic[5], cyc = in.color_intrinsic[6];
+  for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x) {
+    const float u = ((float)x - cxd) / fxd * fxc + cxc, v = ((float)y - cyd) / fyd * fyc + cyc;
+    const long cx = lrintf(u), cy = lrintf(v);
+    lut[(size_t)y * W + x] = (cx >= 0 && cy >= 0 && cx < (long)in.color_width && cy < (long)in.color_height) ? (int32_t)(cy * in.color_width + cx) : -1;
+  }
+}
+
+void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vector<int32_t>& lut, bool use_color, uint64_t f0, uint32_t n, Chunk& c, unsigned threads) {
+  const size_t px = (size_t)in.depth_width * in.depth_height;
+  c.n = n; c.rc = 0; c.poses.assign((size_t)n * 16, 0.f);
+  std::atomic<uint32_t> next{0}; std::atomic<int> rc{0};
+  auto work = [&]() {
+    std::vector<uint8_t> col(use_color ? (size_t)in.color_width * in.color_height * 3 : 0);
+    for (;;) {
+      const uint32_t i = next.fetch_add(1);
+      if (i >= n || rc.load()) break;
+      scn_sens_frame_meta(s, f0 + i, &c.poses[(size_t)i * 16], nullptr, nullptr, nullptr, nullptr);
+      if (c.poses[(size_t)i * 16] == -INFINITY) continue;                        // skipped by the integrator anyway
+      int r = scn_sens_frame_depth_u16(s, f0 + i, c.depth + (size_t)i * px);
+      if (!r && use_color) {
+        r = scn_sens_frame_color_rgb8(s, f0 + i, col.data());
+        if (!r) { uint8_t* o = c.rgb + (size_t)i * px * 3;
+          for (size_t p = 0; p < px; ++p) { const int32_t q = lut[p]; if (q >= 0) { o[3 * p] = col[3 * q]; o[3 * p + 1] = col[3 * q + 1]; o[3 * p + 2] = col[3 * q + 2]; } else o[3 * p] = o[3 * p + 1] = o[3 * p + 2] = 0; } }
+      }
+      if (r) { rc.store(r); }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  c.rc = rc.load();
+  if (c.rc) c.err = scn_last_error();
+}
+
+}  // namespace
+
+extern "C" int scn_fuse_main(int argc, const char** argv) {
+  std::vector<std::string> params; std::string sens_path, out_path;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a.size() > 5 && a.substr(a.size() - 5) == ".sens") sens_path = a;
+    else if (!sens_path.empty()) out_path = a;
+    else params.push_back(a);
+  }
+  if (sens_path.empty()) { printf("Usage: fuse <params.txt> [<params2.txt>] <file.sens> [out.ply]\n"); return 255; }
+  if (out_path.empty()) out_path = sens_path.substr(0, sens_path.size() - 5) + "_vh.ply";
+  scn_sens* s = nullptr;
+  if (scn_sens_open(sens_path.c_str(), &s)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; }
+  scn_sens_info_t in; scn_sens_info(s, &in);
+  scn_tsdf_params p; scn_tsdf_default_params(&p);
+  for (const std::string& f : params) if (scn_tsdf_params_from_file(f.c_str(), &p)) { fprintf(stderr, "%s\n", scn_last_error()); scn_sens_close(s); return 1; }
+  p.width = in.depth_width; p.height = in.depth_height; p.depth_shift = in.depth_shift;   // integrate at the stream's depth resolution
+  p.batch_frames = 8;
+  const bool use_color = in.color_compression == 0 || in.color_compression == 2;
+  printf("fusing %s: %llu frames %ux%u, voxel %.4f m, truncation %.3f+%.3f*d\n", sens_path.c_str(), (unsigned long long)in.n_frames, in.depth_width,
+         in.depth_height, p.voxel_size, p.trunc_base, p.trunc_scale);
+  scn_tsdf* vol = nullptr;
+  if (scn_tsdf_create(&p, 0, &vol)) { fprintf(stderr, "%s\n", scn_last_error()); scn_sens_close(s); return 1; }
+  const size_t px = (size_t)in.depth_width * in.depth_height;
+  const uint32_t CH = 32;
+  const unsigned threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  Chunk ch[2];
+  for (Chunk& c : ch) { c.depth = (uint16_t*)scn_host_alloc(CH * px * 2); c.rgb = use_color ? (uint8_t*)scn_host_alloc(CH * px * 3) : nullptr;
+    if (!c.depth || (use_color && !c.rgb)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; } }
+  std::vector<int32_t> lut; if (use_color) build_color_lut(in, lut);
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = 0; uint64_t f = 0; int cur = 0;
+  if (in.n_frames) decode_chunk(s, in, lut, use_color, 0, (uint32_t)std::min<uint64_t>(CH, in.n_frames), ch[0], threads);
+  while (f < in.n_frames && !rc) {
+    Chunk& c = ch[cur];
+    if (c.rc) { fprintf(stderr, "%s\n", c.err.c_str()); rc = 1; break; }
+    // the GPU consumes chunk `cur` asynchronously while the host decodes the next one into the other buffer
+    if (scn_tsdf_integrate_batch(vol, c.n, c.depth, c.rgb, c.poses.data(), in.depth_intrinsic)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }
+    f += c.n;
+    if (f < in.n_frames) decode_chunk(s, in, lut, use_color, f, (uint32_t)std::min<uint64_t>(CH, in.n_frames - f), ch[cur ^ 1], threads);
+    if (scn_tsdf_sync(vol)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }      // chunk `cur` may be overwritten next round
+    cur ^= 1;
+  }
+  const double fuse_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (!rc) {
+    scn_tsdf_stats_t st; scn_tsdf_stats(vol, &st);
+    printf("integrated %llu frames (%llu skipped: invalid pose) in %.3f s = %.1f frames/s incl. decode; %llu blocks, %llu voxel updates\n",
+           (unsigned long long)st.frames_integrated, (unsigned long long)st.frames_skipped, fuse_s, st.frames_integrated / std::max(fuse_s, 1e-9),
+           (unsigned long long)st.blocks_allocated, (unsigned long long)st.voxels_updated);
+    float* xyz = nullptr; uint8_t* rgb = nullptr; uint32_t* tri = nullptr; uint64_t nV = 0, nF = 0;
+    if (scn_tsdf_extract_mesh(vol, &xyz, &rgb, &tri, &nV, &nF) || scn_mesh_save_ply(out_path.c_str(), xyz, use_color ? rgb : nullptr, nV, tri, nF)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+    else printf("mesh written to %s with %llu vertices, %llu faces\n", out_path.c_str(), (unsigned long long)nV, (unsigned long long)nF);
+    scn_free(xyz); scn_free(rgb); scn_free(tri);
+  }
+  for (Chunk& c : ch) { scn_host_free(c.depth); scn_host_free(c.rgb); }
+  scn_tsdf_destroy(vol); scn_sens_close(s);
+  return rc;
+}

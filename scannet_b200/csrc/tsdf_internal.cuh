@@ -1,0 +1,110 @@
+// Internal declarations shared by tsdf.cu (fusion) and mc.cu (meshing): device tables, key packing, hash,
+// and the host-side handle.  Not part of the public ABI.
+#pragma once
+#include <vector>
+
+#include "scn_common.h"
+
+namespace scn_tsdf_detail {
+
+constexpr int kMaxBatch = 32;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kKeyBias = 1 << 20;
+constexpr int kDdaMaxSteps = 48;
+
+struct VolParams {
+  float vs, trunc_base, trunc_scale, dmin, dmax, maxint, inv_range, ws15, inv_bs, depth_shift;
+  int W, H, weight_max, const_w1;
+};
+struct FrameParams {
+  float T[12];       // cam2world rows 0..2
+  float Rt[9];       // world->cam rotation
+  float tinv[3];     // world->cam translation
+  float Avs[9];      // Rt * voxel_size
+  float fx, fy, cx, cy;
+  int src;           // index of the frame inside the depth / rgb source buffers
+  int has_rgb;
+};
+struct BatchParams {
+  FrameParams f[kMaxBatch];
+  int n;
+};
+
+struct Tables {
+  unsigned long long* keys;
+  int* vals;
+  unsigned int* mask;
+  unsigned long long* block_keys;
+  unsigned int* list;
+  unsigned long long* counters;   // [0] heap_count [1],[2] list_count ping-pong [3] N_u [4] N_b [5] error flags
+  uint2* heap;                    // 512 voxels per block
+  unsigned int cap_mask;
+  unsigned int max_blocks;
+};
+
+enum { C_HEAP = 0, C_LIST0 = 1, C_LIST1 = 2, C_NU = 3, C_NB = 4, C_ERR = 5, C_UNION = 6, C_COUNT = 8 };
+
+// ------------------------------------------------------------------------------ device
+__device__ __forceinline__ bool key_ok(int x, int y, int z) {
+  return x >= -kKeyBias && x < kKeyBias && y >= -kKeyBias && y < kKeyBias && z >= -kKeyBias && z < kKeyBias;
+}
+__device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
+  return (unsigned long long)(unsigned)(x + kKeyBias) | ((unsigned long long)(unsigned)(y + kKeyBias) << 21) |
+         ((unsigned long long)(unsigned)(z + kKeyBias) << 42);
+}
+__device__ __forceinline__ void unpack_key(unsigned long long k, int& x, int& y, int& z) {
+  x = (int)(k & 0x1FFFFF) - kKeyBias;
+  y = (int)((k >> 21) & 0x1FFFFF) - kKeyBias;
+  z = (int)((k >> 42) & 0x1FFFFF) - kKeyBias;
+}
+// vec3i hash of mLib (external/mLib/include/core-util/sparseGrid3.h:14-17) + an avalanche so
+// that the power-of-two table mask sees all bits.
+__device__ __forceinline__ unsigned hash_key(unsigned long long k) {
+  int x, y, z;
+  unpack_key(k, x, y, z);
+  unsigned h = ((unsigned)x * 73856093u) ^ ((unsigned)y * 19349669u) ^ ((unsigned)z * 83492791u);
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+
+
+// read-only lookup: heap index of block (x,y,z) or -1
+__device__ __forceinline__ int lookup_block(const Tables& tb, int x, int y, int z) {
+  if (!key_ok(x, y, z)) return -1;
+  const unsigned long long key = pack_key(x, y, z);
+  unsigned slot = hash_key(key) & tb.cap_mask;
+  for (unsigned probe = 0; probe <= tb.cap_mask; ++probe) {
+    const unsigned long long k = tb.keys[slot];
+    if (k == key) return tb.vals[slot];
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & tb.cap_mask;
+  }
+  return -1;
+}
+
+}  // namespace scn_tsdf_detail
+
+struct scn_tsdf {
+  scn_tsdf_params p{};
+  int device = 0;
+  int sm_count = 148;
+  scn_tsdf_detail::VolParams vp{};
+  scn_tsdf_detail::Tables tb{};
+  uint64_t cap = 0;
+  float* dm = nullptr;
+  uint16_t* d_depth[2] = {nullptr, nullptr};     // H2D staging, double buffered
+  uint8_t* d_rgb[2] = {nullptr, nullptr};
+  uint16_t* h_depth[2] = {nullptr, nullptr};     // pinned bounce buffers (pageable callers)
+  uint8_t* h_rgb[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
+  bool buf_used[2] = {false, false};
+  int parity = 0;
+  uint64_t frames_integrated = 0, frames_skipped = 0, frame_bytes = 0, launches = 0;
+  uint64_t chunk_seq = 0;
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // 3 per batch: before alloc, between, after integrate
+  size_t prof_used = 0;
+  float mc_thresh_factor = 10.0f;         // s_SDFMarchingCubeThreshFactor (zParametersScanNet.txt:48)
+};

@@ -99,6 +99,19 @@ class TsdfVolume:
         check(lib().scn_tsdf_stats(self._h, C.byref(s)))
         return s
 
+    def extract_mesh(self):
+        """Marching cubes: returns (xyz float32 [V,3], rgb uint8 [V,3], tri uint32 [F,3])."""
+        xyz = C.POINTER(C.c_float)(); rgb = C.POINTER(C.c_uint8)(); tri = C.POINTER(C.c_uint32)()
+        nv = C.c_uint64(); nf = C.c_uint64()
+        check(lib().scn_tsdf_extract_mesh(self._h, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nf)))
+        V, F = nv.value, nf.value
+        a = np.ctypeslib.as_array(xyz, (max(V * 3, 1),))[: V * 3].copy().reshape(-1, 3)
+        c = np.ctypeslib.as_array(rgb, (max(V * 3, 1),))[: V * 3].copy().reshape(-1, 3)
+        t = np.ctypeslib.as_array(tri, (max(F * 3, 1),))[: F * 3].copy().reshape(-1, 3)
+        for p in (xyz, rgb, tri):
+            lib().scn_free(p)
+        return a, c, t
+
     def download_blocks(self, sort: bool = True):
         """Returns (block_xyz int32 [n,3], voxels VOXEL_DTYPE [n,512]) sorted by packed key."""
         n = C.c_uint64()

@@ -10,13 +10,15 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_gp
 cat $OUT/pytest_gpu_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -5 $OUT/smoke_$TAG.log
 timeout 600 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; tail -c 600 $OUT/bench_ref_$TAG.json
-timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+timeout 900 python bench.py --seg-c5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+for B in 1 16 32; do timeout 600 python bench.py --no-cpu --no-seg --batch $B > $OUT/bench_batch${B}_$TAG.json 2>/dev/null; python -c "
+import json,sys; d=json.load(open('$OUT/bench_batch${B}_$TAG.json')); print('batch $B', round(d['value']), round(d['e2e']['value']), d['roofline']['avg_launch_ms'], d['roofline']['alloc_kernel_ms_total'], d['roofline']['integrate_kernel_ms_total'])"; done
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
-      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu > $OUT/ncu_launch_$TAG.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file $OUT/launches_$TAG.csv \
+      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu --no-seg > $OUT/ncu_launch_$TAG.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 4 -c 2 -f -o $OUT/prof_integrate_$TAG \
-      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu > $OUT/ncu_full_$TAG.log 2>&1
+      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu --no-seg > $OUT/ncu_full_$TAG.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_alloc -s 4 -c 1 -f -o $OUT/prof_alloc_$TAG \
-      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu > $OUT/ncu_full_alloc_$TAG.log 2>&1
+      python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu --no-seg > $OUT/ncu_full_alloc_$TAG.log 2>&1
   tail -3 $OUT/ncu_full_$TAG.log
 fi

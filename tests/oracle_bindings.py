@@ -83,6 +83,9 @@ def tsdf_oracle_lib():
         _tsdf.oracle_tsdf_num_blocks.argtypes = [C.c_void_p]
         _tsdf.oracle_tsdf_counters.argtypes = [C.c_void_p, C.c_void_p]
         _tsdf.oracle_tsdf_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _tsdf.oracle_tsdf_extract_mesh.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
+        _tsdf.oracle_free.argtypes = [C.c_void_p]
+        _tsdf.oracle_mc_table.argtypes = [C.c_void_p, C.c_void_p]
     return _tsdf
 
 
@@ -116,6 +119,19 @@ class OracleTsdf:
         if n:
             tsdf_oracle_lib().oracle_tsdf_export(self._h, xyz.ctypes.data, vox.ctypes.data)
         return xyz, vox
+
+    def extract_mesh(self, thresh_factor: float = 10.0):
+        L = tsdf_oracle_lib()
+        xyz = C.POINTER(C.c_float)(); rgb = C.POINTER(C.c_uint8)(); tri = C.POINTER(C.c_uint32)()
+        nv = C.c_uint64(); nf = C.c_uint64()
+        L.oracle_tsdf_extract_mesh(self._h, thresh_factor, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nf))
+        V, F = nv.value, nf.value
+        a = np.ctypeslib.as_array(xyz, (max(V * 3, 1),))[: V * 3].copy().reshape(-1, 3)
+        c = np.ctypeslib.as_array(rgb, (max(V * 3, 1),))[: V * 3].copy().reshape(-1, 3)
+        t = np.ctypeslib.as_array(tri, (max(F * 3, 1),))[: F * 3].copy().reshape(-1, 3)
+        for p in (xyz, rgb, tri):
+            L.oracle_free(p)
+        return a, c, t
 
     def close(self):
         if self._h:
