@@ -190,13 +190,17 @@ def seg_bench(c5: bool):
         rec = {"verts": int(len(xyz)), "faces": int(len(tri)), "segments": int(len(set(seg.tolist()))), "bit_identical_to_cpu": bool((seg == ref).all()),
                "gpu_path_s": dt, "stages_ms": {k: round(v, 3) for k, v in zip(["h2d", "normals", "weights", "sort", "kruskal_host", "small_merge_host", "gather_d2h_labels", "total"], ms)},
                "sort_kernel_launches": launches, "cpu_port_s": t_port, "cpu_port_kind": "oracle/seg_oracle.c -O2, 1 thread, arrays in memory"}
-        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_segmentator.so")
-        if os.path.exists(ref_so):
+        ref_bin = os.path.join(ROOT, "oracle", "_ref", "segmentator_ref_O2")
+        if os.path.exists(ref_bin):                  # the unmodified reference CLI in a child process (its stdout must not reach ours)
             with tempfile.TemporaryDirectory() as d:
                 p = os.path.join(d, "m.ply"); synth.write_ply(p, xyz, tri)
-                t0 = time.perf_counter(); ids = ob.ref_segment_file(p, len(xyz)); rec["cpu_reference_s"] = time.perf_counter() - t0
-                rec["cpu_reference_kind"] = "unmodified reference segment() incl. tinyply load, -O2, 1 thread"
-                rec["bit_identical_to_reference"] = bool((ids == seg).all())
+                t0 = time.perf_counter(); r = subprocess.run([ref_bin, p], capture_output=True, text=True); rec["cpu_reference_s"] = time.perf_counter() - t0
+                rec["cpu_reference_kind"] = "unmodified reference CLI (load + segment + segs.json), -O2, 1 thread"
+                if r.returncode == 0:
+                    with open(os.path.join(d, "m.0.010000.segs.json")) as fh:
+                        rec["bit_identical_to_reference"] = bool((np.array(json.load(fh)["segIndices"]) == seg).all())
+                t0 = time.perf_counter(); r2 = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "segmentator"), p], capture_output=True, text=True)
+                rec["gpu_cli_s"] = time.perf_counter() - t0
         out[name] = rec
     return out
 

@@ -137,7 +137,7 @@ void oracle_tsdf_destroy(oracle_tsdf* o) {
 }
 
 /* ---- spec step B: ray-band block allocation for one pixel ---------------------------- */
-static void alloc_pixel(oracle_tsdf* o, const float* T, float fx, float fy, float cx, float cy,
+static void alloc_pixel(oracle_tsdf* o, const float* T, float ifx, float ify, float cx, float cy,
                         float inv_bs, int x, int y, float d) {
   const oracle_tsdf_params* p = &o->p;
   if (!(d >= p->depth_min && d <= p->depth_max)) return;
@@ -146,7 +146,7 @@ static void alloc_pixel(oracle_tsdf* o, const float* T, float fx, float fy, floa
   const float zmin = fminf(p->max_integration_distance, d - tr);
   const float zmax = fminf(p->max_integration_distance, d + tr);
   if (zmin >= zmax) return;
-  const float rx = ((float)x - cx) / fx, ry = ((float)y - cy) / fy;
+  const float rx = ((float)x - cx) * ifx, ry = ((float)y - cy) * ify;      /* ifx = 1/fx, ify = 1/fy */
   float A[3], Bp[3];
   for (int e = 0; e < 2; ++e) {
     const float Z = e ? zmax : zmin, X = rx * Z, Y = ry * Z;
@@ -160,9 +160,10 @@ static void alloc_pixel(oracle_tsdf* o, const float* T, float fx, float fy, floa
   for (int i = 0; i < 3; ++i) {
     cell[i] = (int)floorf(A[i]); end[i] = (int)floorf(Bp[i]);
     const float dir = Bp[i] - A[i];
-    if (dir > 0.0f)      { step[i] = 1;  tmax[i] = ((float)(cell[i] + 1) - A[i]) / dir; tdelta[i] = 1.0f / dir; }
-    else if (dir < 0.0f) { step[i] = -1; tmax[i] = ((float)cell[i] - A[i]) / dir;       tdelta[i] = -1.0f / dir; }
-    else                 { step[i] = 0;  tmax[i] = INFINITY; tdelta[i] = INFINITY; }
+    const float eps = 9.5367431640625e-07f;                        /* 2^-20: flatter than this = parallel to the axis */
+    if (dir >= eps)       { const float inv = 1.0f / dir; step[i] = 1;  tmax[i] = ((float)(cell[i] + 1) - A[i]) * inv; tdelta[i] = inv; }
+    else if (dir <= -eps) { const float inv = 1.0f / dir; step[i] = -1; tmax[i] = ((float)cell[i] - A[i]) * inv;       tdelta[i] = -inv; }
+    else                  { step[i] = 0;  tmax[i] = INFINITY; tdelta[i] = INFINITY; }
   }
   for (int it = 0; it < 48; ++it) {
     touch_block(o, cell[0], cell[1], cell[2]);
@@ -196,7 +197,7 @@ static uint64_t integrate_block(oracle_tsdf* o, int32_t idx, const float* Rt, co
     for (int i = 0; i < 3; ++i)
       pc[i] = fmaf((float)lz, Avs[3 * i + 2], fmaf((float)ly, Avs[3 * i + 1], fmaf((float)lx, Avs[3 * i + 0], base[i])));
     const float z = pc[2];
-    if (!(z > 0.0f)) continue;
+    if (!(z >= 0.015625f)) continue;                              /* 2^-6 m */
     const float rz = 1.0f / z;
     const float u = fmaf(pc[0] * rz, fx, cx), v = fmaf(pc[1] * rz, fy, cy);
     const long ix = lrintf(u), iy = lrintf(v);                 /* round-half-even */
@@ -247,9 +248,10 @@ int oracle_tsdf_integrate(oracle_tsdf* o, const uint16_t* depth, const uint8_t* 
     tinv[i] = -((Rt[3 * i + 0] * T[3] + Rt[3 * i + 1] * T[7]) + Rt[3 * i + 2] * T[11]);
   for (int i = 0; i < 9; ++i) Avs[i] = Rt[i] * p->voxel_size;
   const float inv_bs = 1.0f / (8.0f * p->voxel_size);
+  const float ifx = 1.0f / fx, ify = 1.0f / fy;
   /* step B (sequential: the touched SET does not depend on order) */
   for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
-    alloc_pixel(o, T, fx, fy, cx, cy, inv_bs, x, y, o->dm[y * W + x]);
+    alloc_pixel(o, T, ifx, ify, cx, cy, inv_bs, x, y, o->dm[y * W + x]);
   /* step C (blocks are independent) */
   uint64_t n_upd = 0;
   const int64_t nt = (int64_t)o->n_touched;

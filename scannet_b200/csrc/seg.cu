@@ -394,15 +394,99 @@ __global__ void k_children(const unsigned* __restrict__ segS, const unsigned* __
   }
 }
 
+// ------------------------------------------------------------------------------ replay pruning
+// In BOTH sequential passes an edge whose (unordered) endpoint pair already occurred earlier in sorted order is a
+// provable no-op: if the earlier copy joined its components this one finds a == b; if the earlier copy was rejected
+// then (Kruskal) one of its components had threshold < w and is frozen for every later, heavier edge (a component's
+// threshold only changes when it merges, which needs w <= threshold), or (small-segment pass) both components already
+// had >= segMinVerts vertices and sizes only grow.  Self-loops are no-ops too.  Dropping them halves the host replay
+// for a manifold mesh (every interior edge is emitted once per adjacent face) without changing a single id.
+__global__ void k_pair_first(const Rec* __restrict__ rec, const unsigned* __restrict__ tri, const Edge12* __restrict__ src, size_t nE,
+                             unsigned long long* __restrict__ tkeys, unsigned* __restrict__ tmin, unsigned tmask) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE) return;
+  unsigned a, b;
+  if (tri) edge_ends(tri, rec[j].i, a, b); else { a = (unsigned)src[rec[j].i].a; b = (unsigned)src[rec[j].i].b; }
+  if (a == b) return;
+  const unsigned lo = min(a, b), hi = max(a, b);
+  const unsigned long long key = ((unsigned long long)hi << 32) | lo;
+  unsigned h = (lo * 73856093u) ^ (hi * 19349669u); h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+  unsigned slot = h & tmask;
+  for (;;) {
+    const unsigned long long k = tkeys[slot];
+    if (k == key) break;
+    if (k == ~0ull) { const unsigned long long old = atomicCAS(&tkeys[slot], ~0ull, key); if (old == ~0ull || old == key) break; }
+    slot = (slot + 1) & tmask;
+  }
+  atomicMin(&tmin[slot], (unsigned)j);
+}
+__global__ void k_pair_keep(const Rec* __restrict__ rec, const unsigned* __restrict__ tri, const Edge12* __restrict__ src, size_t nE,
+                            const unsigned long long* __restrict__ tkeys, const unsigned* __restrict__ tmin, unsigned tmask,
+                            unsigned* __restrict__ keep) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE) return;
+  unsigned a, b;
+  if (tri) edge_ends(tri, rec[j].i, a, b); else { a = (unsigned)src[rec[j].i].a; b = (unsigned)src[rec[j].i].b; }
+  unsigned kp = 0;
+  if (a != b) {
+    const unsigned lo = min(a, b), hi = max(a, b);
+    const unsigned long long key = ((unsigned long long)hi << 32) | lo;
+    unsigned h = (lo * 73856093u) ^ (hi * 19349669u); h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    unsigned slot = h & tmask;
+    while (tkeys[slot] != key) slot = (slot + 1) & tmask;
+    kp = tmin[slot] == (unsigned)j;
+  }
+  keep[j] = kp;
+}
+__global__ void k_compact_edges(const Rec* __restrict__ rec, const unsigned* __restrict__ tri, const Edge12* __restrict__ src, size_t nE,
+                                const unsigned* __restrict__ keep, const unsigned* __restrict__ pos, Edge12* __restrict__ out) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nE || !keep[j]) return;
+  const Rec r = rec[j];
+  unsigned a, b;
+  if (tri) edge_ends(tri, r.i, a, b); else { a = (unsigned)src[r.i].a; b = (unsigned)src[r.i].b; }
+  Edge12 e; e.w = r.w; e.a = (int)a; e.b = (int)b;
+  out[pos[j]] = e;
+}
+
 // ------------------------------------------------------------------------------ host side
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
   scn::fail(SCN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return SCN_ERR_CUDA; } } while (0)
 
+// Workspace: a per-thread cached device arena (bump allocator).  cudaMalloc/cudaFree cost ~0.1-1 ms each and
+// synchronise the device; with ~25 buffers per call they dominated small meshes.  The arena is reset at the start of
+// every top-level call and regrown to a single chunk when a call overflowed it.
+struct Arena {
+  struct Chunk { char* p; size_t cap; };
+  std::vector<Chunk> chunks; size_t used = 0, total_req = 0; int dev = -1;
+  void reset() {
+    int d = 0; cudaGetDevice(&d);
+    if (d != dev || chunks.size() > 1) {
+      for (Chunk& c : chunks) cudaFree(c.p);
+      chunks.clear();
+      if (d == dev && total_req) { Chunk c{nullptr, total_req + (total_req >> 3) + (1u << 20)}; if (cudaMalloc(&c.p, c.cap) == cudaSuccess) chunks.push_back(c); }
+      dev = d;
+    }
+    used = 0; total_req = 0;
+  }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255); if (!bytes) bytes = 256;
+    total_req += bytes;
+    if (!chunks.empty() && used + bytes <= chunks.back().cap) { void* r = chunks.back().p + used; used += bytes; return r; }
+    Chunk c{nullptr, std::max(bytes, size_t(8) << 20)};
+    if (cudaMalloc(&c.p, c.cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    chunks.push_back(c); used = bytes;
+    return c.p;
+  }
+};
+thread_local Arena g_arena;
+struct PinnedBuf { void* p = nullptr; size_t cap = 0; void* get(size_t n) { if (n > cap) { if (p) cudaFreeHost(p); p = nullptr; cap = 0; if (cudaHostAlloc(&p, n + (n >> 3), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; } cap = n + (n >> 3); } return p; } };
+thread_local PinnedBuf g_pinned;
+
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
   template <typename T> T* as() { return (T*)p; }
-  int alloc(size_t bytes) { if (bytes == 0) bytes = 16; return cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1; }
+  int alloc(size_t bytes) { p = g_arena.alloc(bytes); return p ? 0 : -1; }
 };
 
 thread_local float g_timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -474,31 +558,65 @@ int device_introsort(Rec* A, size_t n, cudaStream_t st, int forced_depth = 0) {
   return SCN_OK;
 }
 
-// Sequential replay on the host (segmentator.cpp:71-91 Kruskal with adaptive threshold; :236-250).
-struct UfElt { int rank, p, size; };
+// Sequential replay on the host (segmentator.cpp:71-91 Kruskal with adaptive threshold; :236-250) over the pruned
+// records.  One 16-byte element per vertex (the threshold sits next to the root fields it is read with) and software
+// prefetch of the endpoints a few edges ahead: the loop is bound by cache misses on random vertices.
+struct UfElt { int rank, p, size; float thr; };
 inline int uf_find(UfElt* u, int x) { int y = x; while (y != u[y].p) y = u[y].p; u[x].p = y; return y; }
 inline void uf_join(UfElt* u, int x, int y) {
   if (u[x].rank > u[y].rank) { u[y].p = x; u[x].size += u[y].size; }
   else { u[x].p = y; u[y].size += u[x].size; if (u[x].rank == u[y].rank) u[y].rank++; }
 }
+constexpr size_t kPrefetch = 24;
 void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<UfElt>& u) {
   u.resize(nV);
-  std::vector<float> thr(nV, c);
-  for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; }
+  for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; u[i].thr = c; }
+  UfElt* U = u.data();
   for (size_t i = 0; i < nE; ++i) {
-    int a = uf_find(u.data(), e[i].a), b = uf_find(u.data(), e[i].b);
-    if (a != b && e[i].w <= thr[a] && e[i].w <= thr[b]) {
-      uf_join(u.data(), a, b);
-      a = uf_find(u.data(), a);
-      thr[a] = e[i].w + (c / (float)u[a].size);
+    if (i + kPrefetch < nE) { __builtin_prefetch(U + e[i + kPrefetch].a); __builtin_prefetch(U + e[i + kPrefetch].b); }
+    int a = uf_find(U, e[i].a), b = uf_find(U, e[i].b);
+    if (a != b && e[i].w <= U[a].thr && e[i].w <= U[b].thr) {
+      uf_join(U, a, b);
+      a = uf_find(U, a);
+      U[a].thr = e[i].w + (c / (float)U[a].size);
     }
   }
 }
 void host_small_merge(const Edge12* e, size_t nE, int min_verts, std::vector<UfElt>& u) {
+  UfElt* U = u.data();
   for (size_t j = 0; j < nE; ++j) {
-    const int a = uf_find(u.data(), e[j].a), b = uf_find(u.data(), e[j].b);
-    if (a != b && (u[a].size < min_verts || u[b].size < min_verts)) uf_join(u.data(), a, b);
+    if (j + kPrefetch < nE) { __builtin_prefetch(U + e[j + kPrefetch].a); __builtin_prefetch(U + e[j + kPrefetch].b); }
+    const int a = uf_find(U, e[j].a), b = uf_find(U, e[j].b);
+    if (a != b && (U[a].size < min_verts || U[b].size < min_verts)) uf_join(U, a, b);
   }
+}
+
+// Device: drop provable no-op records (see k_pair_first), copy the survivors to pinned host memory.  Returns the
+// pruned, still weight-sorted records in *out (pointer into a cached pinned buffer) and their count.
+int prune_and_download(const Rec* dRec, const unsigned* dTri, const Edge12* dSrc, size_t nE, cudaStream_t st, const Edge12** out, size_t* n_out) {
+  *out = nullptr; *n_out = 0;
+  if (!nE) return SCN_OK;
+  size_t cap = 1; while (cap < 2 * nE) cap <<= 1;
+  DevBuf dK, dM, dKeep, dPos, dOut, dScr;
+  if (dK.alloc(cap * 8) || dM.alloc(cap * 4) || dKeep.alloc(nE * 4) || dPos.alloc((nE + 1) * 4) || dOut.alloc(nE * 12) || dScr.alloc(scn::scan_scratch_elems(nE) * 4))
+    return scn::fail(SCN_ERR_CUDA, "cudaMalloc (replay pruning workspace)");
+  CK(cudaMemsetAsync(dK.p, 0xFF, cap * 8, st));
+  CK(cudaMemsetAsync(dM.p, 0xFF, cap * 4, st));
+  const unsigned g = (unsigned)((nE + 255) / 256);
+  k_pair_first<<<g, 256, 0, st>>>(dRec, dTri, dSrc, nE, dK.as<unsigned long long>(), dM.as<unsigned>(), (unsigned)(cap - 1));
+  k_pair_keep<<<g, 256, 0, st>>>(dRec, dTri, dSrc, nE, dK.as<unsigned long long>(), dM.as<unsigned>(), (unsigned)(cap - 1), dKeep.as<unsigned>());
+  scn::exclusive_scan_u32(dKeep.as<unsigned>(), dPos.as<unsigned>(), nE, dScr.as<unsigned>(), st);
+  k_compact_edges<<<g, 256, 0, st>>>(dRec, dTri, dSrc, nE, dKeep.as<unsigned>(), dPos.as<unsigned>(), dOut.as<Edge12>());
+  unsigned nk = 0;
+  CK(cudaMemcpyAsync(&nk, dPos.as<unsigned>() + nE, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  void* h = g_pinned.get((size_t)nk * 12 + 16);
+  if (!h) return scn::fail(SCN_ERR_CUDA, "cudaHostAlloc (%u records)", nk);
+  CK(cudaMemcpyAsync(h, dOut.p, (size_t)nk * 12, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  *out = (const Edge12*)h; *n_out = nk;
+  return SCN_OK;
 }
 
 struct Timer {
@@ -516,6 +634,7 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return scn::fail(SCN_ERR_CUDA, "no CUDA device: the Segmentator kernels have no CPU fallback");
   Timer total, lapt;
+  g_arena.reset();
   const size_t nE = 3 * nF;
   for (uint64_t i = 0; i < 3 * nF; ++i) if (tri[i] >= nV) return scn::fail(SCN_ERR_FORMAT, "face %llu references vertex %u >= %llu", (unsigned long long)(i / 3), tri[i], (unsigned long long)nV);
   cudaStream_t st = nullptr;
@@ -552,20 +671,21 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   if (rc) return rc;
   CK(cudaStreamSynchronize(st));
   g_timings[3] = lapt.lap();
-  std::vector<Edge12> hE(nE);
-  if (nE) {
+  if (edges_sorted && nE) {                            // full sorted array: parity tests only
     k_gather_edges<<<(unsigned)((nE + B - 1) / B), B, 0, st>>>(dRec.as<Rec>(), dTri.as<unsigned>(), nE, dE12.as<Edge12>());
-    CK(cudaMemcpy(hE.data(), dE12.p, nE * 12, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(edges_sorted, dE12.p, nE * 12, cudaMemcpyDeviceToHost));
+    lapt.lap();
   }
-  CK(cudaGetLastError());
+  const Edge12* hE = nullptr; size_t nK = 0;
+  rc = prune_and_download(dRec.as<Rec>(), dTri.as<unsigned>(), nullptr, nE, st, &hE, &nK);
+  if (rc) return rc;
   g_timings[6] = lapt.lap();
-  if (edges_sorted && nE) memcpy(edges_sorted, hE.data(), nE * 12);
   std::vector<UfElt> u;
-  host_kruskal(hE.data(), nE, nV, kthr, u);
+  host_kruskal(hE, nK, nV, kthr, u);
   g_timings[4] = lapt.lap();
   if (roots_after_kruskal) for (size_t q = 0; q < nV; ++q) { int y = (int)q; while (y != u[y].p) y = u[y].p; roots_after_kruskal[q] = y; }
   lapt.lap();
-  host_small_merge(hE.data(), nE, min_verts, u);
+  host_small_merge(hE, nK, min_verts, u);
   g_timings[5] = lapt.lap();
   for (size_t q = 0; q < nV; ++q) seg_out[q] = uf_find(u.data(), (int)q);
   g_timings[6] += lapt.lap();
@@ -597,6 +717,7 @@ int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c, in
   for (int64_t i = 0; i < n_edges; ++i)
     if (he[i].a < 0 || he[i].a >= n_verts || he[i].b < 0 || he[i].b >= n_verts) return scn::fail(SCN_ERR_ARG, "edge %lld endpoint out of range", (long long)i);
   const size_t nE = (size_t)n_edges;
+  g_arena.reset();
   DevBuf dSrc, dDst, dRec;
   if (dSrc.alloc(nE * 12) || dDst.alloc(nE * 12) || dRec.alloc(nE * 8)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc");
   cudaStream_t st = nullptr;
@@ -611,8 +732,11 @@ int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c, in
     CK(cudaMemcpy(he, dDst.p, nE * 12, cudaMemcpyDeviceToHost));
   }
   CK(cudaGetLastError());
+  const Edge12* hK = nullptr; size_t nK = 0;
+  rc = prune_and_download(dRec.as<Rec>(), nullptr, dSrc.as<Edge12>(), nE, st, &hK, &nK);
+  if (rc) return rc;
   std::vector<UfElt> u;
-  host_kruskal(he, nE, (size_t)n_verts, c, u);
+  host_kruskal(hK, nK, (size_t)n_verts, c, u);
   for (int v = 0; v < n_verts; ++v) {
     int y = v; while (y != u[y].p) y = u[y].p;
     if (roots_out) roots_out[v] = y;

@@ -22,6 +22,7 @@ struct FrameParams {
   float tinv[3];     // world->cam translation
   float Avs[9];      // Rt * voxel_size
   float fx, fy, cx, cy;
+  float ifx, ify;    // 1/fx, 1/fy (correctly rounded, host)
   int src;           // index of the frame inside the depth / rgb source buffers
   int has_rgb;
 };
@@ -42,7 +43,7 @@ struct Tables {
   unsigned int max_blocks;
 };
 
-enum { C_HEAP = 0, C_LIST0 = 1, C_LIST1 = 2, C_NU = 3, C_NB = 4, C_ERR = 5, C_UNION = 6, C_COUNT = 8 };
+enum { C_HEAP = 0, C_LIST0 = 1, C_LIST1 = 2, C_NU = 3, C_NB = 4, C_ERR = 5, C_UNION = 6, C_WORK = 7, C_COUNT = 8 };
 
 // ------------------------------------------------------------------------------ device
 __device__ __forceinline__ bool key_ok(int x, int y, int z) {
