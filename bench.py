@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--color", action="store_true", help="also fuse colour")
     ap.add_argument("--no-seg", action="store_true", help="skip the Segmentator side benchmark")
     ap.add_argument("--seg-c5", action="store_true", help="also run the 2M-vertex Segmentator case")
+    ap.add_argument("--tma-kernel", action="store_true", help="force the cp.async.bulk staged integrate kernel (SCN_TSDF_KERNEL_TMA)")
+    ap.add_argument("--column-kernel", action="store_true", help="force the register-resident column kernel (SCN_TSDF_KERNEL_COLUMN)")
     ap.add_argument("--simple-kernel", action="store_true", help="use the plain 2-voxel/thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -245,7 +247,8 @@ def main():
 
     def make_volume(flags=0):
         p = tsdf.default_params(batch_frames=args.batch, max_blocks=1 << 20, hash_slots=1 << 22,
-                                flags=flags | (tsdf.KERNEL_SIMPLE if args.simple_kernel else 0))
+                                flags=flags | (tsdf.KERNEL_SIMPLE if args.simple_kernel else 0) | (tsdf.KERNEL_TMA if args.tma_kernel else 0) |
+                                (tsdf.KERNEL_COLUMN if args.column_kernel else 0))
         return tsdf.TsdfVolume(p, device=local, stream=torch.cuda.current_stream().cuda_stream)
 
     barrier = grp.barrier
@@ -316,6 +319,14 @@ def main():
         per_launch_ms = integ_ms / max(n_batches, 1)
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         actual = (union_blocks * 8192.0) / (integ_ms * 1e-3) / 1e9 if integ_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as fh:
+                tj = json.load(fh)
+            if args.batch == 8:
+                traffic = tj["dram_bytes_per_launch"].get("k_integrate_col")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": Wm,
             "ms_per_step": ms_dev / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,8 +340,9 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": F * frame_bytes, "d2h_bytes_per_step": 64,
                     "ms_per_step": ms_e2e / S},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_integrate_col", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/latest_traffic.json (ncu dram__bytes read+write per launch, batch 8)" if traffic else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_ms,
                          "launches": int(n_batches),
                          "actual_block_traffic_gbs": actual,

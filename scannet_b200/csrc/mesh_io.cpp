@@ -115,6 +115,16 @@ int load_ply(const std::string& path, std::vector<float>& xyz, std::vector<uint3
           }
         }
         pos += rec * el.count;
+      } else if (is_f && el.props.size() == 1 && el.props[0].is_list && psize(el.props[0].list_type) == 1 && psize(el.props[0].type) == 4 &&
+                 pos + 13 * el.count <= n && !big) {
+        // the VCGLIB / ScanNet layout: `list uchar int vertex_indices`, 13-byte records when every face is a triangle
+        bool all3 = true;
+        for (size_t i = 0; i < el.count; ++i) if (d[pos + 13 * i] != 3) { all3 = false; break; }
+        if (all3) {
+          tri.resize(el.count * 3);
+          for (size_t i = 0; i < el.count; ++i) memcpy(&tri[3 * i], d + pos + 13 * i + 1, 12);
+          pos += 13 * el.count;
+        } else return scn::fail(SCN_ERR_UNSUPPORTED, "only triangle meshes are supported (segmentator.cpp:136)");
       } else {
         for (size_t i = 0; i < el.count; ++i) {
           for (const PProp& p : el.props) {
@@ -302,13 +312,15 @@ int scn_segmentator_main(int argc, const char** argv) {
   std::vector<int32_t> comps(nV);
   if (scn_segment_mesh(xyz, nV, tri, nF, kthr, segMinVerts, comps.data(), 0)) { std::cerr << scn_last_error() << std::endl; scn_free(xyz); scn_free(tri); return 1; }
   scn_free(xyz); scn_free(tri);
-  std::unordered_set<int> ids(comps.begin(), comps.end());
+  // number of distinct ids (the reference fills an unordered_set, segmentator.cpp:279-282); ids are vertex indices < nV
+  std::vector<uint8_t> seen(nV ? nV : 1, 0); size_t n_ids = 0;
+  for (int32_t c : comps) if (!seen[(size_t)c]) { seen[(size_t)c] = 1; ++n_ids; }
   const std::string baseName = plyFile.substr(0, plyFile.find_last_of("."));
   const int lastslash = (int)plyFile.find_last_of("/");
   const std::string scanId = lastslash > 0 ? baseName.substr(lastslash) : baseName;
   const std::string segFile = baseName + "." + std::to_string(kthr) + ".segs.json";
   if (scn_write_segs_json(segFile.c_str(), scanId.c_str(), kthr, segMinVerts, comps.data(), comps.size())) { std::cerr << scn_last_error() << std::endl; return 1; }
-  printf("Segmentation written to %s with %lu segments\n", segFile.c_str(), (unsigned long)ids.size());
+  printf("Segmentation written to %s with %lu segments\n", segFile.c_str(), (unsigned long)n_ids);
   return 0;
 }
 

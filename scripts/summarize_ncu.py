@@ -86,6 +86,22 @@ def main():
         for f in sorted(os.listdir(g)):
             if f.endswith(f"_{tag}.ncu-rep"):
                 fh.write(f"## {f} (ncu --set full)\n\n"); summarize_rep(os.path.join(g, f), fh)
+    # DRAM traffic per launch of the dominant kernel, for bench.py's roofline.traffic
+    import json
+    tr = {}
+    for f in sorted(os.listdir(g)):
+        if f.endswith(f"_{tag}.ncu-rep"):
+            rows = ncu_csv(os.path.join(g, f), "raw"); hdr = rows[0]
+            for r in rows[2:]:
+                name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0]
+                def val(k):
+                    v = float(r[hdr.index(k)]); u = rows[1][hdr.index(k)]
+                    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+                tr.setdefault(name, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    if tr:
+        with open(os.path.join(p, "latest_traffic.json"), "w") as fh:
+            json.dump({"tag": tag, "source": "ncu --set full, bench.py --steps 2 --warmup 1 --frames-per-step 48 (batch 8)",
+                       "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in tr.items()}}, fh, indent=1)
     for f in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"gpu_{tag}.txt", f"pytest_gpu_{tag}.log", f"smoke_{tag}.log"):
         s = os.path.join(g, f)
         if os.path.exists(s):

@@ -103,6 +103,16 @@ def test_simple_kernel_variant(built):
     assert_identical(*run_both(p, D, C, P, K))
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("batch,flag", [(1, 0), (2, 0), (5, tsdf.KERNEL_TMA), (3, tsdf.KERNEL_COLUMN)])
+def test_tma_staged_kernel_variant(built, batch, flag):
+    """cp.async.bulk staged kernel (default for batches of <= 2 frames, forced with SCN_TSDF_KERNEL_TMA) — same bits"""
+    p = tsdf.default_params(width=160, height=120, max_blocks=1 << 15, hash_slots=1 << 17, batch_frames=batch, flags=flag)
+    D, C, P, K = synth.make_frames(7, seed=12, width=160, height=120, loop_frames=150, noise_mm=1.0, drop=0.03)
+    assert_identical(*run_both(p, D, C, P, K))
+    assert_identical(*run_both(p, D, None, P, K, batch_api=False))
+
+
 def test_capacity_error_is_reported(built):
     p = tsdf.default_params(width=160, height=120, max_blocks=64, hash_slots=256, batch_frames=1)
     D, C, P, K = synth.make_frames(1, seed=3, width=160, height=120)
