@@ -34,16 +34,16 @@ struct BatchParams {
 struct Tables {
   unsigned long long* keys;
   int* vals;
-  unsigned int* mask;
+  unsigned int* mask;             // view of the batch parity in flight (host passes mask_base + parity*cap)
   unsigned long long* block_keys;
-  unsigned int* list;
+  unsigned int* list;             // view of the batch parity in flight
   unsigned long long* counters;   // [0] heap_count [1],[2] list_count ping-pong [3] N_u [4] N_b [5] error flags
   uint2* heap;                    // 512 voxels per block
   unsigned int cap_mask;
   unsigned int max_blocks;
 };
 
-enum { C_HEAP = 0, C_LIST0 = 1, C_LIST1 = 2, C_NU = 3, C_NB = 4, C_ERR = 5, C_UNION = 6, C_WORK = 7, C_COUNT = 8 };
+enum { C_HEAP = 0, C_LIST0 = 1, C_LIST1 = 2, C_NU = 3, C_NB = 4, C_ERR = 5, C_UNION = 6, C_WORK0 = 7, C_WORK1 = 8, C_DONE0 = 9, C_DONE1 = 10, C_COUNT = 16 };
 
 // ------------------------------------------------------------------------------ device
 __device__ __forceinline__ bool key_ok(int x, int y, int z) {
@@ -97,7 +97,11 @@ struct scn_tsdf {
   uint8_t* d_rgb[2] = {nullptr, nullptr};
   uint16_t* h_depth[2] = {nullptr, nullptr};     // pinned bounce buffers (pageable callers)
   uint8_t* h_rgb[2] = {nullptr, nullptr};
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, alloc_stream = nullptr;
+  cudaEvent_t ev_alloc_done[2]{}, ev_integ_done[2]{}, ev_input{};
+  bool parity_used[2] = {false, false};
+  unsigned int* mask_base = nullptr; unsigned int* list_base = nullptr;   // 2 x cap, 2 x max_blocks
+  int reserve_ctas = 4;                          // integrate CTAs per SM left free so the next batch's k_alloc can co-run
   bool own_stream = false;
   cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
   bool buf_used[2] = {false, false};
@@ -105,7 +109,7 @@ struct scn_tsdf {
   uint64_t frames_integrated = 0, frames_skipped = 0, frame_bytes = 0, launches = 0;
   uint64_t chunk_seq = 0;
   bool profile = false;
-  std::vector<cudaEvent_t> prof_events;   // 3 per batch: before alloc, between, after integrate
+  std::vector<cudaEvent_t> prof_events;   // 4 per batch: around k_alloc (allocation stream), around the integrate kernel
   size_t prof_used = 0;
   float mc_thresh_factor = 10.0f;         // s_SDFMarchingCubeThreshFactor (zParametersScanNet.txt:48)
 };
