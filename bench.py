@@ -353,7 +353,7 @@ def main():
                                  "block per launch) lower than the algorithmic figure, so frac may exceed 1"},
             "clocks": clocks,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # CPU baseline: rank 0 at N=1 only
             line["cpu_baseline"] = cpu_arm(args)
         if world == 1 and not args.no_seg:
             try:
