@@ -48,8 +48,9 @@ def measured_peak_hbm():
 # ----------------------------------------------------------------------------- synthetic stream
 def scene_poses(n, seed, loop):
     from scannet_b200 import synth
-    size = (6.0 + 0.5 * (seed % 3), 5.0 + 0.4 * (seed % 4), 3.0)
-    sc = synth.BoxRoomScene(size=size, seed=seed, width=W, height=H)
+    # every rank fuses its own scene (different sphere layout per seed) in a room of the same size along the same
+    # camera loop, so per-GPU work is the same to within a few percent and the N-GPU numbers measure scaling, not scenes
+    sc = synth.BoxRoomScene(size=(6.0, 5.0, 3.0), seed=seed, width=W, height=H)
     P = np.stack([sc.camera_pose(i, loop) for i in range(n)]).astype(np.float32)
     return sc, P
 
@@ -231,6 +232,7 @@ def main():
     from scannet_b200 import dist as sdist
     from scannet_b200 import tsdf
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the single JSON line
     rank, world, local = sdist.env_rank()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
