@@ -22,7 +22,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) in
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
 $(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scannet_b200.h | $(OBJDIR)
-	/usr/bin/g++ -O2 -std=c++17 -fPIC -Wall -Wno-unused-function -Wno-misleading-indentation -ffp-contract=off -c $< -o $@
+	/usr/bin/g++ -O3 -std=c++17 -fPIC -Wall -Wno-unused-function -Wno-misleading-indentation -ffp-contract=off -c $< -o $@
 
 $(LIB): $(OBJS) | $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ccbin /usr/bin/g++ -cudart static

@@ -206,6 +206,43 @@ def seg_bench(c5: bool):
     return out
 
 
+def sens_bench(n_frames=120):
+    """SensReader decode throughput (R3/R4) vs the compiled reference, 1 thread, and the decode-inclusive `fuse` CLI
+    (.sens -> TSDF -> marching cubes -> PLY) on a synthetic 640x480 zlib-depth stream."""
+    import ctypes as C
+    import tempfile
+    from scannet_b200 import synth
+    from scannet_b200.sens import SensFile
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        sc, P = scene_poses(n_frames, 3, 1000)
+        D = np.stack([sc.render(P[i], noise_mm=1.0, frame_seed=i)[0] for i in range(n_frames)])
+        p = os.path.join(d, "s.sens")
+        synth.write_sens(p, D, None, P, sc.intrinsics(), depth_comp=1, color_comp=0)
+        s = SensFile(p)
+        t0 = time.perf_counter()
+        for i in range(n_frames):
+            s.depth(i)
+        out["depth_decode_fps_1thread"] = n_frames / (time.perf_counter() - t0)
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_sens.so")
+        if os.path.exists(ref_so):
+            L = C.CDLL(ref_so); L.ref_sens_open.restype = C.c_void_p; L.ref_sens_open.argtypes = [C.c_char_p]
+            L.ref_sens_depth.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+            r = L.ref_sens_open(p.encode()); buf = np.zeros((H, W), np.uint16)
+            t0 = time.perf_counter()
+            for i in range(n_frames):
+                L.ref_sens_depth(r, i, buf.ctypes.data)
+            out["reference_depth_decode_fps_1thread"] = n_frames / (time.perf_counter() - t0)
+        prm = os.path.join(d, "p.txt")
+        with open(prm, "w") as fh:
+            fh.write("s_SDFVoxelSize = 0.004f;\ns_SDFTruncation = 0.02f;\ns_SDFTruncationScale = 0.01f;\n")
+        t0 = time.perf_counter()
+        r = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "fuse"), prm, p], capture_output=True, text=True)
+        out["fuse_cli_wall_s"] = time.perf_counter() - t0
+        out["fuse_cli_stdout"] = [ln for ln in r.stdout.splitlines() if ln.startswith(("integrated", "mesh written"))]
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -360,8 +397,12 @@ def main():
         if world == 1 and not args.no_seg:
             try:
                 line["segmentator"] = seg_bench(args.seg_c5)
-            except Exception as e:          # the side benchmark must never take the headline line down
+            except Exception as e:          # the side benchmarks must never take the headline line down
                 line["segmentator"] = {"error": repr(e)}
+            try:
+                line["sens"] = sens_bench()
+            except Exception as e:
+                line["sens"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     grp.close()
 

@@ -25,13 +25,35 @@ const uint8_t kZig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11,4,5,12,19,26,
                                29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63,
                                63,63,63,63,63,63,63,63,63,63,63,63,63,63,63};
 
+constexpr int kFastBits = 9;
 struct HuffTab {
   bool present = false;
   int maxcode[18]; int valptr[17]; int mincode[17]; uint8_t vals[256];
+  uint16_t fast[1 << kFastBits];          // (symbol << 4) | length for codes of <= 9 bits, 0xFFFF = longer code
+  int16_t fast_ac[1 << kFastBits];        // AC tables: (value << 8) | (run << 4) | (code+magnitude bits) when both fit in 9 bits, else 0
+  void build_fast_ac() {
+    for (int i = 0; i < (1 << kFastBits); ++i) {
+      fast_ac[i] = 0;
+      const uint16_t e = fast[i];
+      if (e == 0xFFFF) continue;
+      const int rs = e >> 4, len = e & 15, run = rs >> 4, mag = rs & 15;
+      if (mag && len + mag <= kFastBits) {
+        int k = ((i << len) & ((1 << kFastBits) - 1)) >> (kFastBits - mag);
+        if (k < (1 << (mag - 1))) k -= (1 << mag) - 1;                       // extend
+        if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)((k * 256) + (run * 16) + (len + mag));
+      }
+    }
+  }
   bool build(const uint8_t* counts, const uint8_t* symbols, int nsym) {
     int code = 0, k = 0;
+    for (int i = 0; i < (1 << kFastBits); ++i) fast[i] = 0xFFFF;
     for (int l = 1; l <= 16; ++l) {
       valptr[l] = k; mincode[l] = code;
+      if (l <= kFastBits)
+        for (int j = 0; j < counts[l - 1]; ++j) {
+          const int c = (code + j) << (kFastBits - l);
+          for (int f = 0; f < (1 << (kFastBits - l)); ++f) fast[c + f] = (uint16_t)((symbols[k + j] << 4) | l);
+        }
       code += counts[l - 1]; k += counts[l - 1];
       if (code > (1 << l)) return false;
       maxcode[l] = counts[l - 1] ? code - 1 : -1;
@@ -64,6 +86,8 @@ struct Bits {
   int get(int k) { if (k == 0) return 0; if (cnt < k) fill(); const int v = (int)(buf >> (32 - k)); buf <<= k; cnt -= k; return v; }
   int decode(const HuffTab& h) {
     if (cnt < 16) fill();
+    const uint16_t e = h.fast[buf >> (32 - kFastBits)];
+    if (e != 0xFFFF) { const int l = e & 15; buf <<= l; cnt -= l; return e >> 4; }
     int code = 0;
     for (int l = 1; l <= 16; ++l) {
       code = (code << 1) | (int)(buf >> 31); buf <<= 1; --cnt;
@@ -96,6 +120,7 @@ inline uint8_t clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (
   p3 = p3 * F2F(-1.961570560f); p4 = p4 * F2F(-0.390180644f);                        \
   t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
 
+__attribute__((target_clones("avx2", "default")))
 void idct8x8(uint8_t* out, int stride, const short* d) {
   int val[64];
   for (int i = 0; i < 8; ++i) {
@@ -155,6 +180,11 @@ inline void ycc_to_rgb(uint8_t* out, int y, int cbv, int crv) {
   out[0] = clamp8(r); out[1] = clamp8(g); out[2] = clamp8(b);
 }
 
+__attribute__((target_clones("avx2", "default")))
+void ycc_row_to_rgb(uint8_t* o, const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int W) {
+  for (int i = 0; i < W; ++i) ycc_to_rgb(o + 3 * i, y[i], cb[i], cr[i]);
+}
+
 }  // namespace
 
 namespace scn {
@@ -192,6 +222,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         for (int i = 0; i < 16; ++i) tot += s[1 + i];
         if (tc > 1 || th > 3 || tot > 256 || sl < (size_t)(17 + tot)) return fail(SCN_ERR_FORMAT, "bad DHT");
         if (!(tc ? hac[th] : hdc[th]).build(s + 1, s + 17, tot)) return fail(SCN_ERR_FORMAT, "bad code lengths");
+        if (tc) hac[th].build_fast_ac();
         s += 17 + tot; sl -= 17 + tot;
       }
     } else if (m == 0xDD) { if (sl < 2) return fail(SCN_ERR_FORMAT, "bad DRI"); restart = (s[0] << 8) | s[1]; }
@@ -237,8 +268,19 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         const int diff = t ? extend(br.get(t), t) : 0;
         c.dc_pred += diff;
         blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
+        const HuffTab& ha = hac[c.ta];
         for (int k = 1; k < 64;) {
-          const int rs = br.decode(hac[c.ta]);
+          if (br.cnt < 16) br.fill();
+          const int fa = ha.fast_ac[br.buf >> (32 - kFastBits)];
+          if (fa) {                                             // short code + small coefficient in one lookup
+            k += (fa >> 4) & 15;
+            const int used = fa & 15;
+            br.buf <<= used; br.cnt -= used;
+            const int z = kZig[k++];
+            blk[z] = (short)((fa >> 8) * quant[c.tq][z]);
+            continue;
+          }
+          const int rs = br.decode(ha);
           if (rs < 0) return false;
           const int sz = rs & 15, r = rs >> 4;
           if (sz == 0) { if (rs != 0xF0) break; k += 16; }
@@ -306,7 +348,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
       if (++r.ystep >= r.vs) { r.ystep = 0; r.l0 = r.l1; if (++r.ypos < comp[k].y) r.l1 += comp[k].w2; }
     }
     uint8_t* o = out + (size_t)j * W * 3;
-    if (ncomp == 3) for (int i = 0; i < W; ++i) ycc_to_rgb(o + 3 * i, row[0][i], row[1][i], row[2][i]);
+    if (ncomp == 3) ycc_row_to_rgb(o, row[0], row[1], row[2], W);
     else for (int i = 0; i < W; ++i) o[3 * i] = o[3 * i + 1] = o[3 * i + 2] = row[0][i];
   }
   return SCN_OK;

@@ -31,63 +31,88 @@ void zlib_deflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out);
 }  // namespace scn
 
 // ------------------------------------------------------------------------------ inflate (RFC 1950/1951)
+// Table-driven decoder: 64-bit bit reservoir, 10-bit first-level lookup per Huffman code (longer codes walk the
+// canonical ranges), literals/matches written straight into a pre-sized output buffer.
 namespace {
 
-struct BitReader {
-  const uint8_t* p; size_t n, pos = 0; uint32_t buf = 0; int cnt = 0; bool bad = false;
-  BitReader(const uint8_t* d, size_t len) : p(d), n(len) {}
-  uint32_t bits(int k) {
-    while (cnt < k) { if (pos >= n) { bad = true; return 0; } buf |= (uint32_t)p[pos++] << cnt; cnt += 8; }
-    const uint32_t v = buf & ((k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1)); buf >>= k; cnt -= k; return v;
-  }
-};
-struct Huff {
-  uint16_t count[16]; uint16_t symbol[288];
-  void build(const uint8_t* len, int n) {
-    memset(count, 0, sizeof(count));
-    for (int i = 0; i < n; ++i) count[len[i]]++;
-    count[0] = 0;
-    uint16_t offs[16]; offs[1] = 0;
-    for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
-    for (int i = 0; i < n; ++i) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
-  }
-  int decode(BitReader& br) const {
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l <= 15; ++l) {
-      code |= (int)br.bits(1);
-      if (br.bad) return -1;
-      const int c = count[l];
-      if (code - c < first) return symbol[index + (code - first)];
-      index += c; first += c; first <<= 1; code <<= 1;
-    }
-    return -1;
-  }
-};
 const uint16_t kLenBase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
 const uint8_t kLenExtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
 const uint16_t kDistBase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
 const uint8_t kDistExtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
 
+struct BitIn {
+  const uint8_t* p; const uint8_t* end; uint64_t buf = 0; int cnt = 0; int pad = 0; bool bad = false;
+  BitIn(const uint8_t* d, size_t n) : p(d), end(d + n) {}
+  // past the end zero bytes are fed (the look-ahead may legitimately run a few bytes over); a stream that actually
+  // consumes them is truncated: `bad` is raised once more than one reservoir of padding has been supplied
+  inline void fill() { while (cnt <= 56) { if (p < end) buf |= (uint64_t)(*p++) << cnt; else if (++pad > 16) bad = true; cnt += 8; } }
+  inline uint32_t peek(int k) { if (cnt < k) fill(); return (uint32_t)(buf & ((1ull << k) - 1)); }
+  inline void drop(int k) { buf >>= k; cnt -= k; }
+  inline uint32_t bits(int k) { if (k == 0) return 0; const uint32_t v = peek(k); drop(k); return v; }
+  inline size_t overrun() const { return cnt < 0 ? 1 : 0; }
+};
+
+constexpr int kFast = 10;
+struct Huff {
+  uint16_t fast[1 << kFast];            // (symbol << 4) | length, 0 = not in table
+  uint16_t count[16]; uint16_t symbol[288]; int first_code[16], first_sym[16]; int max_len = 0;
+  static inline uint32_t rev(uint32_t c, int n) { uint32_t r = 0; for (int i = 0; i < n; ++i) { r = (r << 1) | (c & 1); c >>= 1; } return r; }
+  bool build(const uint8_t* len, int n) {
+    memset(count, 0, sizeof(count)); memset(fast, 0, sizeof(fast)); max_len = 0;
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    count[0] = 0;
+    int code = 0, k = 0; uint16_t offs[16]; int next_code[16];
+    for (int l = 1; l < 16; ++l) {
+      first_code[l] = code; first_sym[l] = k; offs[l] = (uint16_t)k; next_code[l] = code;
+      if (count[l] > (1 << l)) return false;
+      code = (code + count[l]) << 1; k += count[l];
+      if (count[l]) max_len = l;
+    }
+    for (int i = 0; i < n; ++i) if (len[i]) {
+      const int l = len[i];
+      symbol[offs[l]++] = (uint16_t)i;
+      const int c = next_code[l]++;
+      if (l <= kFast) {                                        // deflate codes are packed LSB first: index by the reversed code
+        const uint32_t r = rev((uint32_t)c, l);
+        for (uint32_t j = r; j < (1u << kFast); j += (1u << l)) fast[j] = (uint16_t)((i << 4) | l);
+      }
+    }
+    return true;
+  }
+  inline int decode(BitIn& br) const {
+    const uint32_t look = br.peek(15);
+    const uint16_t e = fast[look & ((1u << kFast) - 1)];
+    if (e) { br.drop(e & 15); return e >> 4; }
+    int code = 0;
+    for (int l = 1; l <= max_len; ++l) {
+      code = (code << 1) | (int)((look >> (l - 1)) & 1);
+      const int idx = code - first_code[l];
+      if (idx >= 0 && idx < count[l]) { br.drop(l); return symbol[first_sym[l] + idx]; }
+    }
+    return -1;
+  }
+};
+
 }  // namespace
 
 int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t size_hint) {
   out.clear();
-  if (size_hint) out.reserve(size_hint);
   if (n < 6) return -1;
   if ((src[0] & 0x0F) != 8 || ((src[0] << 8) | src[1]) % 31 != 0 || (src[1] & 0x20)) return -1;
-  BitReader br(src + 2, n - 2);
-  Huff lit, dist;
+  BitIn br(src + 2, n - 2);
+  out.resize(size_hint ? size_hint : std::max<size_t>(n * 4, 1 << 16));
+  size_t op = 0;
+  auto ensure = [&](size_t extra) { if (op + extra > out.size()) out.resize(std::max(out.size() * 2, op + extra)); };
+  static thread_local Huff lit, dist;
   for (;;) {
     const uint32_t final = br.bits(1), type = br.bits(2);
-    if (br.bad) return -1;
     if (type == 0) {
-      br.buf = 0; br.cnt = 0;
-      if (br.pos + 4 > br.n) return -1;
-      const uint32_t len = br.p[br.pos] | (br.p[br.pos + 1] << 8), nlen = br.p[br.pos + 2] | (br.p[br.pos + 3] << 8);
-      br.pos += 4;
-      if ((len ^ 0xFFFF) != nlen || br.pos + len > br.n) return -1;
-      out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
-      br.pos += len;
+      br.drop(br.cnt & 7);                                  // to the byte boundary
+      const uint32_t len = br.bits(16), nlen = br.bits(16);
+      if ((len ^ 0xFFFF) != nlen) return -1;
+      ensure(len);
+      for (uint32_t i = 0; i < len; ++i) { out[op++] = (uint8_t)br.bits(8); }
+      if (br.bad) return -1;
     } else if (type == 1 || type == 2) {
       uint8_t lens[320];
       if (type == 1) {
@@ -98,11 +123,11 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
         dist.build(lens, 30);
       } else {
         const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
-        if (br.bad || nlen > 286 || ndist > 30) return -1;
+        if (nlen > 286 || ndist > 30) return -1;
         static const uint8_t order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
         uint8_t cl[19]; memset(cl, 0, sizeof(cl));
         for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
-        Huff clh; clh.build(cl, 19);
+        Huff clh; if (!clh.build(cl, 19)) return -1;
         int idx = 0;
         while (idx < nlen + ndist) {
           const int sym = clh.decode(br);
@@ -117,29 +142,32 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
             while (rep--) lens[idx++] = (uint8_t)val;
           }
         }
-        lit.build(lens, nlen);
-        dist.build(lens + nlen, ndist);
+        if (!lit.build(lens, nlen) || !dist.build(lens + nlen, ndist)) return -1;
       }
       for (;;) {
         const int sym = lit.decode(br);
         if (sym < 0) return -1;
-        if (sym < 256) out.push_back((uint8_t)sym);
+        if (sym < 256) { if (op == out.size()) { if (br.bad) return -1; ensure(1); } out[op++] = (uint8_t)sym; }
         else if (sym == 256) break;
         else {
           const int li = sym - 257;
           if (li >= 29) return -1;
-          const int len = kLenBase[li] + (int)br.bits(kLenExtra[li]);
+          const size_t len = kLenBase[li] + br.bits(kLenExtra[li]);
           const int ds = dist.decode(br);
           if (ds < 0 || ds >= 30) return -1;
           const size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
-          if (br.bad || d > out.size()) return -1;
-          const size_t start = out.size() - d;
-          for (int i = 0; i < len; ++i) out.push_back(out[start + i]);
+          if (d > op) return -1;
+          ensure(len);
+          uint8_t* dst = out.data() + op; const uint8_t* from = dst - d;
+          if (d >= len) memcpy(dst, from, len); else for (size_t i = 0; i < len; ++i) dst[i] = from[i];
+          op += len;
         }
+        if (br.bad) return -1;
       }
     } else return -1;
     if (final) break;
   }
+  out.resize(op);
   return 0;
 }
 
