@@ -26,5 +26,6 @@ def test_two_rank_gloo_reduction(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    lines = sorted(l for l in r.stdout.splitlines() if l.startswith("rank="))
+    import re                                   # the two ranks share one pipe: their lines can interleave
+    lines = sorted(re.findall(r"rank=\d world=\d seed=\d+ frames=\d+ ms=[0-9.]+?(?=rank=|\s|$)", r.stdout))
     assert lines == ["rank=0 world=2 seed=10 frames=2001 ms=75.0", "rank=1 world=2 seed=11 frames=2001 ms=75.0"]

@@ -102,3 +102,18 @@ def test_tsdf_oracle_geometry(built):
     dwall = np.minimum.reduce([q[:, 0], q[:, 1], q[:, 2], sc.size[0] - q[:, 0], sc.size[1] - q[:, 1], sc.size[2] - q[:, 2]])
     dsph = np.minimum.reduce([np.abs(np.linalg.norm(q - c, axis=1) - r) for c, r in sc.spheres])
     assert (np.minimum(dwall, dsph) < 0.012).mean() > 0.99
+
+
+def test_tsdf_spec_frozen(built):
+    """the TSDF/marching-cubes oracle reproduces the committed hashes (scripts/make_tsdf_golden.py): guards this
+    repo's own spec against drift — it is NOT a pin against the reference, which has no TSDF source"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ob.ROOT, "scripts", "make_tsdf_golden.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    with open(os.path.join(G, "tsdf_spec_golden.json")) as fh:
+        gold = json.load(fh)
+    for c in gold["cases"]:
+        r = mk.run({k: c[k] for k in ("name", "wh", "frames", "seed", "loop", "noise", "drop", "inv", "color", "over")})
+        for k, v in r.items():
+            assert c[k] == v, (c["name"], k)

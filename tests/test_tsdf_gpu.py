@@ -122,3 +122,28 @@ def test_capacity_error_is_reported(built):
     with pytest.raises(ScnError):
         vol.sync()
     vol.close()
+
+
+def test_gpu_matches_committed_spec_hashes(built):
+    """same seeded cases as tests/golden/tsdf_spec_golden.json, hashed from the CUDA path's own output"""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(root, "scripts", "make_tsdf_golden.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    with open(os.path.join(root, "tests", "golden", "tsdf_spec_golden.json")) as fh:
+        gold = json.load(fh)
+    for c in gold["cases"]:
+        w, h = c["wh"]
+        D, C, P, K = synth.make_frames(c["frames"], seed=c["seed"], width=w, height=h, loop_frames=c["loop"], noise_mm=c["noise"],
+                                       drop=c["drop"], invalid_pose_every=c["inv"])
+        p = tsdf.default_params(width=w, height=h, max_blocks=1 << 15, hash_slots=1 << 17, batch_frames=4, **c["over"])
+        vol = tsdf.TsdfVolume(p, device=0)
+        vol.integrate_batch(D, C if c["color"] else None, P, K); vol.sync()
+        xyz, vox = vol.download_blocks()
+        mx, mc_, mt = vol.extract_mesh()
+        assert hashlib.sha256(xyz.tobytes() + vox.tobytes()).hexdigest() == c["volume_sha256"], c["name"]
+        assert hashlib.sha256(mx.tobytes() + mc_.tobytes() + mt.tobytes()).hexdigest() == c["mesh_sha256"], c["name"]
+        vol.close()
