@@ -251,7 +251,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=100)
-    ap.add_argument("--batch", type=int, default=8, help="frames fused per block residency (scn_tsdf_params.batch_frames)")
+    ap.add_argument("--batch", type=int, default=16, help="frames fused per block residency (scn_tsdf_params.batch_frames)")
     ap.add_argument("--loop", type=int, default=1000, help="frames per camera loop of the synthetic trajectory")
     ap.add_argument("--cpu-frames", type=int, default=40, help="bounded CPU sample (frames)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -362,7 +362,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as fh:
                 tj = json.load(fh)
-            if args.batch == 8:
+            if args.batch == tj.get("batch", 8):
                 traffic = tj["dram_bytes_per_launch"].get("k_integrate_col")
         except Exception:
             pass

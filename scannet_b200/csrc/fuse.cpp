@@ -79,7 +79,7 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   scn_tsdf_params p; scn_tsdf_default_params(&p);
   for (const std::string& f : params) if (scn_tsdf_params_from_file(f.c_str(), &p)) { fprintf(stderr, "%s\n", scn_last_error()); scn_sens_close(s); return 1; }
   p.width = in.depth_width; p.height = in.depth_height; p.depth_shift = in.depth_shift;   // integrate at the stream's depth resolution
-  p.batch_frames = 8;
+  p.batch_frames = 16;
   const bool use_color = in.color_compression == 0 || in.color_compression == 2;
   printf("fusing %s: %llu frames %ux%u, voxel %.4f m, truncation %.3f+%.3f*d\n", sens_path.c_str(), (unsigned long long)in.n_frames, in.depth_width,
          in.depth_height, p.voxel_size, p.trunc_base, p.trunc_scale);

@@ -102,7 +102,7 @@ struct scn_tsdf {
   bool parity_used[2] = {false, false};
   unsigned int* mask_base = nullptr; unsigned int* list_base = nullptr;   // 2 x cap, 2 x max_blocks
   int alloc_group = 4;                           // frames of a batch walked by one k_alloc CTA (shared-memory key map reuse)
-  int reserve_ctas = 4;                          // integrate CTAs per SM left free so the next batch's k_alloc can co-run
+  int reserve_ctas = 0;                          // integrate CTAs per SM left free for the next batch's k_alloc (measured: 0 is best, SCN_TSDF_RESERVE)
   bool own_stream = false;
   cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
   bool buf_used[2] = {false, false};

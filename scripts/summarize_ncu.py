@@ -100,7 +100,7 @@ def main():
                 tr.setdefault(name, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
     if tr:
         with open(os.path.join(p, "latest_traffic.json"), "w") as fh:
-            json.dump({"tag": tag, "source": "ncu --set full, bench.py --steps 2 --warmup 1 --frames-per-step 48 (batch 8)",
+            json.dump({"tag": tag, "source": "ncu --set full, bench.py --steps 2 --warmup 1 --frames-per-step 48 (default batch)", "batch": 16,
                        "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in tr.items()}}, fh, indent=1)
     for f in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"gpu_{tag}.txt", f"pytest_gpu_{tag}.log", f"smoke_{tag}.log"):
         s = os.path.join(g, f)
