@@ -154,6 +154,9 @@ typedef struct {
   uint64_t max_blocks;                /* 8^3 voxel blocks in the heap (4 KiB each)  s_hashNumSDFBlocks  */
   uint32_t batch_frames;              /* frames fused per block residency, 1..32                        */
   uint32_t flags;                     /* SCN_TSDF_* */
+  uint32_t depth_filter;              /* s_depthFilter: bilateral pre-filter of the depth map (zParametersBundlingScanNet.txt:74) */
+  float    depth_sigma_d;             /* s_depthSigmaD  (:72) pixels                                    */
+  float    depth_sigma_r;             /* s_depthSigmaR  (:73) metres                                    */
 } scn_tsdf_params;
 
 #define SCN_TSDF_NO_STATS   1u        /* skip the per-launch counters (N_u, N_b) */
@@ -209,6 +212,12 @@ int  scn_tsdf_extract_mesh(scn_tsdf* t, float** xyz, uint8_t** rgb, uint32_t** t
 /* PLY writer in the VCGLIB layout Segmentator reads (Server/config/scan_stages.json:33-37). */
 int  scn_mesh_save_ply(const char* path, const float* xyz, const uint8_t* rgb, uint64_t n_verts,
                        const uint32_t* tri, uint64_t n_faces);
+/* Depth bilateral filter as BundleFusion applies it before integration (zParametersBundlingScanNet.txt:72-74); the only
+ * in-tree statement of the kernel is AnnotationTools/Filter2dAnnotations/filter.cu:210-247 (bilateralFilterFloatMapDevice),
+ * whose arithmetic (float domain weight, double range weight, -inf = invalid) is reproduced.  depth: w*h uint16 (host);
+ * out_metres: w*h float (host), -inf where invalid.  Used inside scn_tsdf_integrate* when params.depth_filter != 0. */
+int  scn_depth_bilateral_filter(const uint16_t* depth, uint32_t w, uint32_t h, float depth_shift, float sigma_d, float sigma_r,
+                                float* out_metres);
 /* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract. */
 int  scn_fuse_main(int argc, const char** argv);
 

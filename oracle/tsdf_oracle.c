@@ -230,17 +230,35 @@ static uint64_t integrate_block(oracle_tsdf* o, int32_t idx, const float* Rt, co
 /* One frame.  K is the 4x4 row-major depth intrinsic as stored in a .sens header
  * (sensorData.h:300-307): fx=K[0], cx=K[2], fy=K[5], cy=K[6].  Returns 1 if the frame was
  * skipped (invalid pose), 0 otherwise. */
+static int integrate_dm(oracle_tsdf* o, const uint8_t* rgb, const float* T, const float* K);
+
 int oracle_tsdf_integrate(oracle_tsdf* o, const uint16_t* depth, const uint8_t* rgb,
                           const float* T /*cam2world 16*/, const float* K /*16*/) {
   const oracle_tsdf_params* p = &o->p;
   const int W = (int)p->width, H = (int)p->height;
   o->last_updated = o->last_touched = 0;
   if (T[0] == -INFINITY) { o->frames_skipped++; return 1; }
+  /* step A: depth in metres */
+  for (int i = 0; i < W * H; ++i) o->dm[i] = depth[i] == 0 ? 0.0f : (float)depth[i] / p->depth_shift;
+  return integrate_dm(o, rgb, T, K);
+}
+
+/* Same, from an already prepared metres image (-inf or 0 = invalid): the path taken when the depth map went through the
+ * bilateral pre-filter first (the GPU-filtered image is handed in so that the comparison stays bit-exact). */
+int oracle_tsdf_integrate_metres(oracle_tsdf* o, const float* metres, const uint8_t* rgb, const float* T, const float* K) {
+  const int n = (int)o->p.width * (int)o->p.height;
+  o->last_updated = o->last_touched = 0;
+  if (T[0] == -INFINITY) { o->frames_skipped++; return 1; }
+  for (int i = 0; i < n; ++i) o->dm[i] = metres[i] == -INFINITY ? 0.0f : metres[i];
+  return integrate_dm(o, rgb, T, K);
+}
+
+static int integrate_dm(oracle_tsdf* o, const uint8_t* rgb, const float* T, const float* K) {
+  const oracle_tsdf_params* p = &o->p;
+  const int W = (int)p->width, H = (int)p->height;
   const float fx = K[0], cx = K[2], fy = K[5], cy = K[6];
   o->frame_no++;
   o->n_touched = 0;
-  /* step A: depth in metres */
-  for (int i = 0; i < W * H; ++i) o->dm[i] = depth[i] == 0 ? 0.0f : (float)depth[i] / p->depth_shift;
   /* per-frame constants */
   float Rt[9], tinv[3], Avs[9];
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt[3 * i + j] = T[4 * j + i];
@@ -424,3 +442,36 @@ void oracle_tsdf_extract_mesh(const oracle_tsdf* o, float thresh_factor, float**
   *xyz_out = pos; *rgb_out = col; *tri_out = tri; *nv_out = nv2; *nf_out = nt;
 }
 void oracle_free(void* p) { free(p); }
+
+
+/* ------------------------------------------------------------------ depth bilateral filter --------------------
+ * Restatement of bilateralFilterFloatMapDevice, /root/reference/AnnotationTools/Filter2dAnnotations/filter.cu:210-247
+ * (gaussD :201-204 in float, gaussR :191-194 in double), fed as Filter2dAnnotations.cpp:245-256 feeds it
+ * (0 -> -inf, else raw / depthShift).  The reference is a CUDA kernel; exp/expf here are libm's, so the CUDA kernel in
+ * scannet_b200/csrc/filter.cu is compared to a tolerance, not bit for bit. */
+void oracle_bilateral_filter(const uint16_t* depth, int W, int H, float depth_shift, float sigmaD, float sigmaR, float* out) {
+  float* in = (float*)malloc((size_t)W * H * 4);
+  for (int i = 0; i < W * H; ++i) in[i] = depth[i] == 0 ? -INFINITY : (float)depth[i] / depth_shift;
+  const int r = (int)ceil(2.0 * sigmaD);
+  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+    float res = -INFINITY, sum = 0.0f, sumw = 0.0f;
+    const float c = in[y * W + x];
+    if (c != -INFINITY) {
+      for (int m = x - r; m <= x + r; ++m) for (int n = y - r; n <= y + r; ++n) {
+        if (m < 0 || n < 0 || m >= W || n >= H) continue;
+        const float cur = in[n * W + m];
+        if (cur == -INFINITY) continue;
+        const int dx = m - x, dy = n - y;
+        const float gd = expf(-((float)(dx * dx + dy * dy) / (2.0f * sigmaD * sigmaD)));
+        const float dd = cur - c;
+        const float gr = (float)exp(-(dd * dd) / (2.0 * sigmaR * sigmaR));
+        const float w = gd * gr;
+        sumw += w;
+        sum = fmaf(w, cur, sum);
+      }
+      if (sumw > 0.0f) res = sum / sumw;
+    }
+    out[y * W + x] = res;
+  }
+  free(in);
+}

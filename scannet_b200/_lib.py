@@ -24,7 +24,8 @@ class TsdfParams(C.Structure):
                 ("weight_sample", C.c_uint32), ("weight_max", C.c_uint32),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("depth_shift", C.c_float),
                 ("hash_slots", C.c_uint64), ("max_blocks", C.c_uint64),
-                ("batch_frames", C.c_uint32), ("flags", C.c_uint32)]
+                ("batch_frames", C.c_uint32), ("flags", C.c_uint32),
+                ("depth_filter", C.c_uint32), ("depth_sigma_d", C.c_float), ("depth_sigma_r", C.c_float)]
 
 
 class TsdfStats(C.Structure):

@@ -112,5 +112,9 @@ struct scn_tsdf {
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // 4 per batch: around k_alloc (allocation stream), around the integrate kernel
   size_t prof_used = 0;
+  float* filt_raw = nullptr; float* filt_out = nullptr;   // bilateral pre-filter scratch: 2 parities x K frames each (lazy)
   float mc_thresh_factor = 10.0f;         // s_SDFMarchingCubeThreshFactor (zParametersScanNet.txt:48)
 };
+
+// filter.cu: u16 -> metres (-inf invalid) -> bilateral filter for the n frames of a batch, on the allocation stream
+int scn_filter_batch(scn_tsdf* t, int n, const uint16_t* d_depth, const scn_tsdf_detail::BatchParams& bp, int parity, const float** out);

@@ -129,3 +129,12 @@ class TsdfVolume:
             o = np.argsort(key, kind="stable")
             xyz, vox = xyz[o], vox[o]
         return xyz, vox
+
+
+def bilateral_filter(depth: np.ndarray, depth_shift: float = 1000.0, sigma_d: float = 2.0, sigma_r: float = 0.05) -> np.ndarray:
+    """Depth bilateral pre-filter (scn_depth_bilateral_filter): uint16 [H,W] -> float32 metres, -inf = invalid."""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    out = np.zeros(depth.shape, np.float32)
+    check(lib().scn_depth_bilateral_filter(depth.ctypes.data_as(C.c_void_p), C.c_uint32(depth.shape[1]), C.c_uint32(depth.shape[0]),
+                                           C.c_float(depth_shift), C.c_float(sigma_d), C.c_float(sigma_r), out.ctypes.data_as(C.c_void_p)))
+    return out

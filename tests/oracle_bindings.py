@@ -86,6 +86,8 @@ def tsdf_oracle_lib():
         _tsdf.oracle_tsdf_extract_mesh.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
         _tsdf.oracle_free.argtypes = [C.c_void_p]
         _tsdf.oracle_mc_table.argtypes = [C.c_void_p, C.c_void_p]
+        _tsdf.oracle_tsdf_integrate_metres.argtypes = [C.c_void_p] * 5
+        _tsdf.oracle_bilateral_filter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
     return _tsdf
 
 
@@ -106,6 +108,14 @@ class OracleTsdf:
         if rgb is not None:
             rgb = np.ascontiguousarray(rgb, np.uint8); rp = rgb.ctypes.data
         return tsdf_oracle_lib().oracle_tsdf_integrate(self._h, depth.ctypes.data, rp, T.ctypes.data, Kc.ctypes.data)
+
+    def integrate_metres(self, metres, rgb, cam2world, K):
+        m = np.ascontiguousarray(metres, np.float32)
+        T = np.ascontiguousarray(cam2world, np.float32); Kc = np.ascontiguousarray(K, np.float32)
+        rp = None
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, np.uint8); rp = rgb.ctypes.data
+        return tsdf_oracle_lib().oracle_tsdf_integrate_metres(self._h, m.ctypes.data, rp, T.ctypes.data, Kc.ctypes.data)
 
     def counters(self):
         c = np.zeros(6, np.uint64)
@@ -138,3 +148,10 @@ class OracleTsdf:
             tsdf_oracle_lib().oracle_tsdf_destroy(self._h); self._h = None
 
     __del__ = close
+
+
+def oracle_bilateral(depth, depth_shift, sigma_d, sigma_r):
+    depth = np.ascontiguousarray(depth, np.uint16)
+    out = np.zeros(depth.shape, np.float32)
+    tsdf_oracle_lib().oracle_bilateral_filter(depth.ctypes.data, depth.shape[1], depth.shape[0], depth_shift, sigma_d, sigma_r, out.ctypes.data)
+    return out
