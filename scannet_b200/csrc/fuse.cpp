@@ -77,6 +77,7 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   if (scn_sens_open(sens_path.c_str(), &s)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; }
   scn_sens_info_t in; scn_sens_info(s, &in);
   scn_tsdf_params p; scn_tsdf_default_params(&p);
+  p.max_blocks = 1ull << 22; p.hash_slots = 1ull << 24;      // 16 GiB of voxel blocks unless the parameter file says otherwise (s_hashNumSDFBlocks)
   for (const std::string& f : params) if (scn_tsdf_params_from_file(f.c_str(), &p)) { fprintf(stderr, "%s\n", scn_last_error()); scn_sens_close(s); return 1; }
   p.width = in.depth_width; p.height = in.depth_height; p.depth_shift = in.depth_shift;   // integrate at the stream's depth resolution
   p.batch_frames = 16;
