@@ -10,6 +10,7 @@
 //   scn_write_segs_json    writeToJSON (segmentator.cpp:253-266)
 //   scn_segmentator_main   main (segmentator.cpp:268-288): same argv, stdout lines, file naming, exit codes
 //   scn_mesh_save_ply      VCGLIB-layout binary PLY (the layout of gates381.ply / ScanNet *_vh_clean*.ply)
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -306,12 +307,17 @@ int scn_segmentator_main(int argc, const char** argv) {
   const float kthr = argc > 2 ? (float)atof(argv[2]) : 0.01f;
   const int segMinVerts = argc > 3 ? atoi(argv[3]) : 20;
   printf("Segmenting %s with kThresh=%f, segMinVerts=%d ...\n", plyFile.c_str(), kthr, segMinVerts);
+  const bool timing = getenv("SCN_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   float* xyz = nullptr; uint32_t* tri = nullptr; uint64_t nV = 0, nF = 0;
   if (scn_mesh_load(plyFile.c_str(), &xyz, &nV, &tri, &nF)) { std::cerr << scn_last_error() << std::endl; return 1; }
   printf("Read mesh with vertexCount %lu %lu, faceCount %lu %lu\n", (unsigned long)nV, (unsigned long)(nV * 3), (unsigned long)nF, (unsigned long)(nF * 3));
+  const double t_loaded = now();
   std::vector<int32_t> comps(nV);
   if (scn_segment_mesh(xyz, nV, tri, nF, kthr, segMinVerts, comps.data(), 0)) { std::cerr << scn_last_error() << std::endl; scn_free(xyz); scn_free(tri); return 1; }
   scn_free(xyz); scn_free(tri);
+  const double t_segmented = now();
   // number of distinct ids (the reference fills an unordered_set, segmentator.cpp:279-282); ids are vertex indices < nV
   std::vector<uint8_t> seen(nV ? nV : 1, 0); size_t n_ids = 0;
   for (int32_t c : comps) if (!seen[(size_t)c]) { seen[(size_t)c] = 1; ++n_ids; }
@@ -320,6 +326,11 @@ int scn_segmentator_main(int argc, const char** argv) {
   const std::string scanId = lastslash > 0 ? baseName.substr(lastslash) : baseName;
   const std::string segFile = baseName + "." + std::to_string(kthr) + ".segs.json";
   if (scn_write_segs_json(segFile.c_str(), scanId.c_str(), kthr, segMinVerts, comps.data(), comps.size())) { std::cerr << scn_last_error() << std::endl; return 1; }
+  if (timing) {
+    float ms[8]; scn_segment_last_timings(ms);
+    fprintf(stderr, "[timing] load %.3f s, segment %.3f s (h2d %.1f normals %.1f weights %.1f sort %.1f kruskal %.1f small %.1f prune+d2h+labels %.1f ms), json+count %.3f s\n",
+            t_loaded - t_start, t_segmented - t_loaded, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], now() - t_segmented);
+  }
   printf("Segmentation written to %s with %lu segments\n", segFile.c_str(), (unsigned long)n_ids);
   return 0;
 }
