@@ -25,7 +25,7 @@ $(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scannet_b200.h 
 	/usr/bin/g++ -O3 -std=c++17 -fPIC -Wall -Wno-unused-function -Wno-misleading-indentation -ffp-contract=off -c $< -o $@
 
 $(LIB): $(OBJS) | $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ccbin /usr/bin/g++ -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ccbin /usr/bin/g++ -cudart static -lpthread
 
 $(BINDIR)/%: scannet_b200/tools/%_main.cpp $(LIB) | $(BINDIR)
 	/usr/bin/g++ -O2 -std=c++17 -Iinclude -o $@ $< -L$(LIBDIR) -lscannet_b200 -Wl,-rpath,'$$ORIGIN/../lib'

@@ -32,6 +32,8 @@ const char* scn_last_error(void);
 int  scn_version(void);
 /* Number of CUDA devices visible (<0 on error). */
 int  scn_device_count(void);
+/* Creates the CUDA context now (≈0.3 s in a cold process); safe to call from a helper thread while input files are read. */
+int  scn_cuda_warmup(void);
 /* Pinned host memory for frame staging (cudaHostAlloc); integrate calls detect it and skip the bounce copy. */
 void* scn_host_alloc(size_t bytes);
 void  scn_host_free(void* p);

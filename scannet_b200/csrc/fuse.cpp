@@ -73,8 +73,11 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   }
   if (sens_path.empty()) { printf("Usage: fuse <params.txt> [<params2.txt>] <file.sens> [out.ply]\n"); return 255; }
   if (out_path.empty()) out_path = sens_path.substr(0, sens_path.size() - 5) + "_vh.ply";
+  std::thread warm([]() { scn_cuda_warmup(); });          // context creation overlaps reading the .sens file
   scn_sens* s = nullptr;
-  if (scn_sens_open(sens_path.c_str(), &s)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; }
+  const int open_rc = scn_sens_open(sens_path.c_str(), &s);
+  warm.join();
+  if (open_rc) { fprintf(stderr, "%s\n", scn_last_error()); return 1; }
   scn_sens_info_t in; scn_sens_info(s, &in);
   scn_tsdf_params p; scn_tsdf_default_params(&p);
   p.max_blocks = 1ull << 22; p.hash_slots = 1ull << 24;      // 16 GiB of voxel blocks unless the parameter file says otherwise (s_hashNumSDFBlocks)

@@ -469,6 +469,13 @@ struct Arena {
     }
     used = 0; total_req = 0;
   }
+  // make room for `bytes` more in one chunk (called once per top-level call with an upper bound of its needs)
+  void reserve(size_t bytes) {
+    if (!chunks.empty() && used + bytes <= chunks.back().cap) return;
+    Chunk c{nullptr, bytes + (1u << 20)};
+    if (cudaMalloc(&c.p, c.cap) != cudaSuccess) { cudaGetLastError(); return; }   // fall back to piecemeal chunks
+    chunks.push_back(c); used = 0;
+  }
   void* alloc(size_t bytes) {
     bytes = (bytes + 255) & ~size_t(255); if (!bytes) bytes = 256;
     total_req += bytes;
@@ -636,6 +643,7 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   Timer total, lapt;
   g_arena.reset();
   const size_t nE = 3 * nF;
+  g_arena.reserve(80 * nE + 64 * (size_t)nV + (size_t(32) << 20));      // upper bound of every buffer below incl. sort + pruning
   for (uint64_t i = 0; i < 3 * nF; ++i) if (tri[i] >= nV) return scn::fail(SCN_ERR_FORMAT, "face %llu references vertex %u >= %llu", (unsigned long long)(i / 3), tri[i], (unsigned long long)nV);
   cudaStream_t st = nullptr;
   DevBuf dXyz, dTri, dFn, dDeg, dOff, dCur, dCsr, dNrm, dRec, dE12, dScr;
@@ -718,6 +726,7 @@ int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c, in
     if (he[i].a < 0 || he[i].a >= n_verts || he[i].b < 0 || he[i].b >= n_verts) return scn::fail(SCN_ERR_ARG, "edge %lld endpoint out of range", (long long)i);
   const size_t nE = (size_t)n_edges;
   g_arena.reset();
+  g_arena.reserve(96 * nE + (size_t(32) << 20));
   DevBuf dSrc, dDst, dRec;
   if (dSrc.alloc(nE * 12) || dDst.alloc(nE * 12) || dRec.alloc(nE * 8)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc");
   cudaStream_t st = nullptr;
