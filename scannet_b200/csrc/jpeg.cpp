@@ -13,6 +13,7 @@
 // Supported: SOF0/SOF1 8-bit, 1 or 3 components, interleaved and non-interleaved scans, restart markers.
 // Progressive (SOF2) files are rejected with SCN_ERR_UNSUPPORTED.
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -354,8 +355,68 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
   return SCN_OK;
 }
 
-int png_decode_rgb8(const uint8_t*, size_t, uint32_t, uint32_t, uint8_t*) {
-  return fail(SCN_ERR_UNSUPPORTED, "PNG colour frames are not supported (ScanNet .sens files store JPEG, Converter/main.cpp:37)");
+int zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t size_hint);   // sens.cpp
+
+// PNG colour frames (TYPE_PNG, sensorData.h:346-351; decoded by stbi_load_from_memory with 3 requested channels,
+// :609-616).  PNG is lossless, so any conforming decoder returns the reference's bytes; conversions to RGB follow
+// stb_image v2.08 (grey replicated, alpha dropped, palette expanded; 16-bit PNGs are rejected there and here).
+// Non-interlaced images only (Adam7 is rejected).
+int png_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out) {
+  static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+  if (n < 8 || memcmp(d, sig, 8)) return fail(SCN_ERR_FORMAT, "not a PNG");
+  auto be32 = [&](size_t o) { return ((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3]; };
+  uint32_t W = 0, H = 0; int depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, pal;
+  size_t pos = 8; bool have_hdr = false, done = false;
+  while (!done && pos + 12 <= n) {
+    const uint32_t len = be32(pos); const uint8_t* type = d + pos + 4;
+    if (pos + 12 + (size_t)len > n) return fail(SCN_ERR_FORMAT, "truncated PNG chunk");
+    const uint8_t* body = d + pos + 8;
+    if (!memcmp(type, "IHDR", 4)) {
+      if (len < 13) return fail(SCN_ERR_FORMAT, "bad IHDR");
+      W = be32(pos + 8); H = be32(pos + 12); depth = body[8]; ctype = body[9]; interlace = body[12]; have_hdr = true;
+    } else if (!memcmp(type, "PLTE", 4)) pal.assign(body, body + len);
+    else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+    else if (!memcmp(type, "IEND", 4)) done = true;
+    pos += 12 + (size_t)len;
+  }
+  if (!have_hdr || idat.empty()) return fail(SCN_ERR_FORMAT, "PNG without IHDR/IDAT");
+  if (W != want_w || H != want_h) return fail(SCN_ERR_FORMAT, "PNG is %ux%u, header says %ux%u", W, H, want_w, want_h);
+  if (interlace) return fail(SCN_ERR_UNSUPPORTED, "interlaced PNG is not supported");
+  if (depth == 16) return fail(SCN_ERR_UNSUPPORTED, "PNG not supported: 1/2/4/8-bit only");          // as stb_image v2.08
+  if (!(depth == 8 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return fail(SCN_ERR_FORMAT, "bad PNG bit depth");
+  const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (!ch) return fail(SCN_ERR_FORMAT, "bad PNG colour type");
+  const size_t bpp = std::max<size_t>(1, (size_t)ch * depth / 8), stride = ((size_t)W * ch * depth + 7) / 8;
+  std::vector<uint8_t> raw;
+  if (zlib_inflate(idat.data(), idat.size(), raw, (stride + 1) * H) || raw.size() < (stride + 1) * H) return fail(SCN_ERR_FORMAT, "corrupt PNG data");
+  std::vector<uint8_t> prev(stride, 0), cur(stride);
+  for (uint32_t y = 0; y < H; ++y) {
+    const uint8_t* line = raw.data() + (size_t)y * (stride + 1); const int ft = line[0];
+    for (size_t i = 0; i < stride; ++i) {
+      const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+      int pr;
+      switch (ft) {
+        case 0: pr = 0; break; case 1: pr = a; break; case 2: pr = b; break; case 3: pr = (a + b) >> 1; break;
+        case 4: { const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c); pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
+        default: return fail(SCN_ERR_FORMAT, "bad PNG filter");
+      }
+      cur[i] = (uint8_t)(line[1 + i] + pr);
+    }
+    uint8_t* o = out + (size_t)y * W * 3;
+    for (uint32_t x = 0; x < W; ++x) {
+      auto sample = [&](int k) -> int {                       // k-th channel of pixel x as an 8-bit value
+        if (depth == 8) return cur[(size_t)x * ch + k];
+        const size_t bit = (size_t)x * depth; const int v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+        return ctype == 3 ? v : v * (255 / ((1 << depth) - 1));
+      };
+      if (ctype == 3) { const int idx = sample(0); for (int k = 0; k < 3; ++k) o[3 * x + k] = (size_t)(3 * idx + k) < pal.size() ? pal[3 * idx + k] : 0; }
+      else if (ch <= 2) { const uint8_t g = (uint8_t)sample(0); o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = g; }
+      else for (int k = 0; k < 3; ++k) o[3 * x + k] = (uint8_t)sample(k);
+    }
+    prev.swap(cur);
+  }
+  return SCN_OK;
 }
 
 }  // namespace scn

@@ -291,7 +291,7 @@ def write_sens(path, depth: np.ndarray, rgb: np.ndarray | None, poses: np.ndarra
         for i in range(N):
             if color_comp == 0:
                 cb = rgb[i].tobytes()
-            elif color_comp == 2:
+            elif color_comp in (1, 2):                      # PNG / JPEG payload produced by the supplied encoder
                 cb = bytes(jpeg_encoder(rgb[i]))
             else:
                 raise ValueError("color_comp")

@@ -92,6 +92,43 @@ def test_jpeg_subsampling_modes_match_stb(tmp_path, built, sub, wh):
 
 
 @need_ref
+@pytest.mark.parametrize("mode", ["rgb", "rgba", "gray", "palette", "rgb16"])
+def test_png_colour_frames_match_stb(tmp_path, built, mode):
+    """TYPE_PNG colour (sensorData.h:346-351): same RGB bytes as stbi_load_from_memory(..., 3)"""
+    import cv2
+    rng = np.random.default_rng(5); W, H = 53, 37
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    if mode == "rgb":
+        ok, buf = cv2.imencode(".png", img[:, :, ::-1])
+    elif mode == "rgba":
+        ok, buf = cv2.imencode(".png", np.dstack([img[:, :, ::-1], rng.integers(0, 256, (H, W), dtype=np.uint8)]))
+    elif mode == "gray":
+        ok, buf = cv2.imencode(".png", img[:, :, 0])
+    elif mode == "rgb16":
+        ok, buf = cv2.imencode(".png", (img[:, :, ::-1].astype(np.uint16) << 8) | 0x5A)
+    else:
+        from PIL import Image
+        import io
+        b = io.BytesIO(); Image.fromarray(img).quantize(37).save(b, format="PNG"); buf = np.frombuffer(b.getvalue(), np.uint8); ok = True
+    assert ok
+    D = np.full((1, 8, 8), 1000, np.uint16); P = np.eye(4, dtype=np.float32)[None]
+    p = str(tmp_path / "p.sens")
+    synth.write_sens(p, D, np.zeros((1, H, W, 3), np.uint8), P, np.eye(4, dtype=np.float32), depth_comp=0, color_comp=1,
+                     jpeg_encoder=lambda x: bytes(buf))
+    L = ref_lib(); r = L.ref_sens_open(p.encode()); s = SensFile(p)
+    rc = np.zeros((H, W, 3), np.uint8)
+    if mode == "rgb16":                                  # stb_image v2.08 rejects 16-bit PNGs; so do we
+        from scannet_b200 import ScnError
+        assert L.ref_sens_color(r, 0, rc.ctypes.data) != 0
+        with pytest.raises(ScnError):
+            s.color(0)
+    else:
+        assert L.ref_sens_color(r, 0, rc.ctypes.data) == 0
+        assert (s.color(0) == rc).all()
+    L.ref_sens_close(r)
+
+
+@need_ref
 def test_writer_round_trip_through_reference(tmp_path, built):
     """scn_sens_create/add_frame/save -> the reference loads it and decodes identical depth (our deflate, its inflate)."""
     D, Cc, P, K = synth.make_frames(3, seed=4, width=96, height=64, loop_frames=30, noise_mm=1.0)
