@@ -31,6 +31,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+# stdout carries exactly ONE line (the JSON result): everything else that C libraries print on fd 1 (NCCL's version banner,
+# the reference's printf) is diverted to stderr for the life of the process.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 METRIC = "depth frames/sec integrated (640x480, 4 mm voxel)"
 UNIT = "frames/s"
 W, H = 640, 480
@@ -168,7 +178,7 @@ def run_reference(args):
                        "frames_per_step": args.frames_per_step, "voxel_m": 0.004, "truncation_m": "0.02+0.01*d"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- Segmentator side benchmark
@@ -403,7 +413,7 @@ def main():
                 line["sens"] = sens_bench()
             except Exception as e:
                 line["sens"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     grp.close()
 
 
