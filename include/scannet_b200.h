@@ -220,6 +220,38 @@ int  scn_mesh_save_ply(const char* path, const float* xyz, const uint8_t* rgb, u
  * out_metres: w*h float (host), -inf where invalid.  Used inside scn_tsdf_integrate* when params.depth_filter != 0. */
 int  scn_depth_bilateral_filter(const uint16_t* depth, uint32_t w, uint32_t h, float depth_shift, float sigma_d, float sigma_r,
                                 float* out_metres);
+/* ------------------------------------------------------------------------------------------------------------------
+ * segs.json consumers: what the annotation tools do with Segmentator's output.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Reader with the tolerance of AnnotationTools/common/Segmentation.h:57-88: segIndices entries may be JSON ints, uints,
+ * strings of digits, or null (-> 0xFFFFFFFF); params.kThresh / params.segMinVerts default to 0 when absent.
+ * *seg_out is malloc'ed (release with scn_free); scene_id may be NULL. */
+int  scn_segs_load(const char* path, uint32_t** seg_out, uint64_t* n_out, float* k_thresh, uint32_t* seg_min_verts,
+                   char* scene_id, size_t scene_id_cap);
+/* Segmentation::m_segIdsToVertIds (Segmentation.h:70-75) and computeSurfaceAreaPerSegment (Segmentation.h:113-147) in one pass
+ * on the GPU.  Outputs (malloc'ed, scn_free): seg_ids[nS] ascending; vert_offsets[nS+1] + vert_ids[nV]: the vertices of
+ * segment k are vert_ids[vert_offsets[k] .. vert_offsets[k+1]) in ascending order (the reference's push_back order);
+ * area[nS]: sum of Trianglef::getArea (mLib core-graphics/triangle.h:23-35) over the faces whose three corners all lie in the
+ * segment, accumulated in double in ascending face order (the reference adds floats in unordered_map order, so only a
+ * tolerance is meaningful).  xyz/tri/area may be NULL/0 to skip the area. */
+int  scn_segs_aggregate(const uint32_t* seg, uint64_t n_verts, const float* xyz, const uint32_t* tri, uint64_t n_faces,
+                        uint32_t** seg_ids, uint64_t* n_segs, uint64_t** vert_offsets, uint32_t** vert_ids, float** area);
+/* Per-vertex object ids from an aggregation (Visualizer.cpp:284-297): group g lists segment ids
+ * group_segs[group_offsets[g] .. group_offsets[g+1]); every vertex of those segments gets object id g+1, later groups
+ * overwrite earlier ones, vertices of ungrouped segments get 0. */
+int  scn_segs_objects_per_vertex(const uint32_t* seg, uint64_t n_verts, const uint32_t* group_segs, const uint64_t* group_offsets,
+                                 uint64_t n_groups, uint32_t* obj_out);
+/* mLib MeshData::computeVertexNormals (core-mesh/meshData.h:758-782): unit face normals summed per vertex in face order,
+ * then normalised with 1/length — bit-identical to the sequential loop. */
+int  scn_mesh_vertex_normals(const float* xyz, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces, float* normals_out);
+/* Annotation propagation from the decimated to the hi-res mesh (Visualizer::propagateAnnotations, Visualizer.cpp:308-377):
+ * for each destination vertex the 3 nearest LABELLED (obj > 0) source vertices decide its object id — the first of them
+ * that is closer than maxThresh = max(0.01 * largest source bbox extent, 0.05) and whose normal is within normal_thresh
+ * radians wins; otherwise the nearest one's id if all three are within maxThresh and agree; otherwise 0.
+ * The reference searches with an approximate FLANN kd-tree; this is the exact 3-NN (ties by source index). */
+int  scn_propagate_labels(const float* src_xyz, const float* src_normals, const uint32_t* src_obj, uint64_t n_src,
+                          const float* dst_xyz, const float* dst_normals, uint64_t n_dst, float normal_thresh,
+                          uint32_t* dst_obj_out);
 /* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract. */
 int  scn_fuse_main(int argc, const char** argv);
 

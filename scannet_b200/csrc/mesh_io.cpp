@@ -10,6 +10,7 @@
 //   scn_write_segs_json    writeToJSON (segmentator.cpp:253-266)
 //   scn_segmentator_main   main (segmentator.cpp:268-288): same argv, stdout lines, file naming, exit codes
 //   scn_mesh_save_ply      VCGLIB-layout binary PLY (the layout of gates381.ply / ScanNet *_vh_clean*.ply)
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -256,6 +257,48 @@ int load_obj(const std::string& path, std::vector<float>& xyz, std::vector<uint3
   return SCN_OK;
 }
 
+
+// ------------------------------------------------------------------------------ segs.json reader
+// Minimal JSON walker: enough to read what Segmentator (and the annotation tools' re-savers) write, with the
+// value tolerance of Segmentation::getUINT / getFloat (Segmentation.h:158-190).
+struct JsonCur {
+  const char* p; const char* e; std::string err;
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p; }
+  bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
+  bool str(std::string& out) {
+    ws(); if (p >= e || *p != '"') return false; ++p; out.clear();
+    while (p < e && *p != '"') {
+      if (*p == '\\' && p + 1 < e) { ++p; switch (*p) { case 'n': out.push_back('\n'); break; case 't': out.push_back('\t'); break; case 'r': out.push_back('\r'); break;
+        case 'b': out.push_back('\b'); break; case 'f': out.push_back('\f'); break; case 'u': out.push_back('?'); p += (e - p > 4 ? 4 : 0); break; default: out.push_back(*p); } ++p; }
+      else out.push_back(*p++);
+    }
+    if (p >= e) return false; ++p; return true;
+  }
+  bool skip() {                                                            // any value
+    ws(); if (p >= e) return false;
+    if (*p == '"') { std::string t; return str(t); }
+    if (*p == '{' || *p == '[') {
+      const char open = *p, close = open == '{' ? '}' : ']'; ++p;
+      if (eat(close)) return true;
+      for (;;) {
+        if (open == '{') { std::string k; if (!str(k) || !eat(':')) return false; }
+        if (!skip()) return false;
+        if (eat(',')) continue;
+        return eat(close);
+      }
+    }
+    while (p < e && *p != ',' && *p != '}' && *p != ']' && *p != ' ' && *p != '\n' && *p != '\r' && *p != '\t') ++p;   // number / true / false / null
+    return true;
+  }
+  // number | "digits" | null  ->  double (null: nan)
+  bool num(double& v) {
+    ws(); if (p >= e) return false;
+    if (*p == '"') { std::string t; if (!str(t)) return false; v = atof(t.c_str()); return true; }
+    if (e - p >= 4 && !strncmp(p, "null", 4)) { p += 4; v = NAN; return true; }
+    char* end = nullptr; v = strtod(p, &end); if (end == p) return false; p = end; return true;
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -297,6 +340,61 @@ int scn_write_segs_json(const char* path, const char* scene_id, float k_thresh, 
   const bool ok = fwrite(body.data(), 1, body.size(), f) == body.size();
   fclose(f);
   return ok ? SCN_OK : scn::fail(SCN_ERR_IO, "short write on %s", path);
+}
+
+int scn_segs_load(const char* path, uint32_t** seg_out, uint64_t* n_out, float* k_thresh, uint32_t* seg_min_verts, char* scene_id, size_t scene_id_cap) {
+  if (!path || !seg_out || !n_out) return scn::fail(SCN_ERR_ARG, "null argument");
+  *seg_out = nullptr; *n_out = 0; if (k_thresh) *k_thresh = 0.f; if (seg_min_verts) *seg_min_verts = 0; if (scene_id && scene_id_cap) scene_id[0] = 0;
+  FILE* f = fopen(path, "rb");
+  if (!f) return scn::fail(SCN_ERR_IO, "failed to open file %s", path);
+  std::string buf; fseek(f, 0, SEEK_END); const long sz = ftell(f); fseek(f, 0, SEEK_SET);
+  buf.resize(sz > 0 ? (size_t)sz : 0);
+  const bool rd = buf.empty() || fread(&buf[0], 1, buf.size(), f) == buf.size(); fclose(f);
+  if (!rd) return scn::fail(SCN_ERR_IO, "short read on %s", path);
+  JsonCur c{buf.data(), buf.data() + buf.size(), {}};
+  if (!c.eat('{')) return scn::fail(SCN_ERR_FORMAT, "Parse error reading %s at offset 0", path);
+  std::vector<uint32_t> ids; bool have_ids = false;
+  if (!c.eat('}')) for (;;) {
+    std::string key;
+    if (!c.str(key) || !c.eat(':')) return scn::fail(SCN_ERR_FORMAT, "Parse error reading %s at offset %zu", path, (size_t)(c.p - buf.data()));
+    bool ok = true;
+    if (key == "segIndices") {
+      ok = c.eat('['); have_ids = ok;
+      if (ok && !c.eat(']')) for (;;) {
+        double v; c.ws();
+        const bool is_null = c.e - c.p >= 4 && !strncmp(c.p, "null", 4);
+        if (!c.num(v)) { ok = false; break; }
+        ids.push_back(is_null ? 0xFFFFFFFFu : (v < 0 ? (uint32_t)(int32_t)v : (uint32_t)v));      // getUINT: (unsigned)GetInt() for negatives
+        if (c.eat(',')) continue;
+        ok = c.eat(']'); break;
+      }
+    } else if (key == "params") {
+      ok = c.eat('{');
+      if (ok && !c.eat('}')) for (;;) {
+        std::string pk; double v;
+        if (!c.str(pk) || !c.eat(':')) { ok = false; break; }
+        if (pk == "kThresh") { ok = c.num(v); if (ok && k_thresh) *k_thresh = (float)v; }
+        else if (pk == "segMinVerts") { ok = c.num(v); if (ok && seg_min_verts) *seg_min_verts = (uint32_t)v; }
+        else ok = c.skip();
+        if (!ok) break;
+        if (c.eat(',')) continue;
+        ok = c.eat('}'); break;
+      }
+    } else if (key == "sceneId") {
+      std::string v; ok = c.str(v);
+      if (ok && scene_id && scene_id_cap) { strncpy(scene_id, v.c_str(), scene_id_cap - 1); scene_id[scene_id_cap - 1] = 0; }
+    } else ok = c.skip();
+    if (!ok) return scn::fail(SCN_ERR_FORMAT, "Parse error reading %s at offset %zu", path, (size_t)(c.p - buf.data()));
+    if (c.eat(',')) continue;
+    if (!c.eat('}')) return scn::fail(SCN_ERR_FORMAT, "Parse error reading %s at offset %zu", path, (size_t)(c.p - buf.data()));
+    break;
+  }
+  if (!have_ids) return scn::fail(SCN_ERR_FORMAT, "%s has no segIndices member", path);
+  uint32_t* out = (uint32_t*)malloc(std::max<size_t>(ids.size(), 1) * 4);
+  if (!out) return scn::fail(SCN_ERR_ARG, "out of memory");
+  if (!ids.empty()) memcpy(out, ids.data(), ids.size() * 4);
+  *seg_out = out; *n_out = ids.size();
+  return SCN_OK;
 }
 
 int scn_segmentator_main(int argc, const char** argv) {

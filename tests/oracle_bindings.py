@@ -155,3 +155,76 @@ def oracle_bilateral(depth, depth_shift, sigma_d, sigma_r):
     out = np.zeros(depth.shape, np.float32)
     tsdf_oracle_lib().oracle_bilateral_filter(depth.ctypes.data, depth.shape[1], depth.shape[0], depth_shift, sigma_d, sigma_r, out.ctypes.data)
     return out
+
+
+# ---- segs.json consumers (oracle/segs_oracle.c, oracle/ref_shim_mlib.cpp) -------------------------------------
+_segs = _refmlib = None
+
+
+def segs_oracle():
+    global _segs
+    if _segs is None:
+        _segs = _load("oracle/_build/liboracle_segs.so")
+        _segs.oracle_tri_area_mlib.restype = C.c_float
+        _segs.oracle_tri_area_mlib.argtypes = [C.c_void_p] * 3
+        _segs.oracle_segs_aggregate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+        _segs.oracle_objects_per_vertex.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _segs.oracle_vertex_normals_mlib.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        _segs.oracle_propagate_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    return _segs
+
+
+def ref_mlib():
+    global _refmlib
+    if _refmlib is None:
+        _refmlib = _load("oracle/_ref/libref_mlib.so")
+        _refmlib.ref_tri_area.restype = C.c_float
+        _refmlib.ref_tri_area.argtypes = [C.c_void_p] * 3
+        _refmlib.ref_vertex_normals.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    return _refmlib
+
+
+def oracle_segs_aggregate(seg, xyz=None, tri=None):
+    seg = np.ascontiguousarray(seg, np.uint32); nV = len(seg)
+    want = xyz is not None
+    if want:
+        xyz = np.ascontiguousarray(xyz, np.float32); tri = np.ascontiguousarray(tri, np.uint32)
+    ids = np.zeros(max(nV, 1), np.uint32); off = np.zeros(nV + 1, np.uint64); vid = np.zeros(max(nV, 1), np.uint32)
+    area = np.zeros(max(nV, 1), np.float32); nS = C.c_int64()
+    segs_oracle().oracle_segs_aggregate(seg.ctypes.data, nV, xyz.ctypes.data if want else None, tri.ctypes.data if want else None,
+                                        len(tri) if want else 0, ids.ctypes.data, C.addressof(nS), off.ctypes.data, vid.ctypes.data,
+                                        area.ctypes.data if want else None)
+    n = nS.value
+    return dict(seg_ids=ids[:n].copy(), offsets=off[:n + 1].copy(), vert_ids=vid[:nV].copy(), area=area[:n].copy() if want else None)
+
+
+def oracle_objects_per_vertex(seg, groups):
+    seg = np.ascontiguousarray(seg, np.uint32)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(list(g), np.uint32) for g in groups]) if groups else np.zeros(1, np.uint32), np.uint32)
+    offs = np.zeros(len(groups) + 1, np.uint64); offs[1:] = np.cumsum([len(list(g)) for g in groups]) if groups else []
+    out = np.zeros(len(seg), np.uint32)
+    segs_oracle().oracle_objects_per_vertex(seg.ctypes.data, len(seg), flat.ctypes.data, offs.ctypes.data, len(groups), out.ctypes.data)
+    return out
+
+
+def oracle_vertex_normals_mlib(xyz, tri):
+    xyz = np.ascontiguousarray(xyz, np.float32); tri = np.ascontiguousarray(tri, np.uint32)
+    out = np.zeros((len(xyz), 3), np.float32)
+    segs_oracle().oracle_vertex_normals_mlib(xyz.ctypes.data, len(xyz), tri.ctypes.data, len(tri), out.ctypes.data)
+    return out
+
+
+def ref_vertex_normals_mlib(xyz, tri):
+    xyz = np.ascontiguousarray(xyz, np.float32); tri = np.ascontiguousarray(tri, np.uint32)
+    out = np.zeros((len(xyz), 3), np.float32)
+    ref_mlib().ref_vertex_normals(xyz.ctypes.data, len(xyz), tri.ctypes.data, len(tri), out.ctypes.data)
+    return out
+
+
+def oracle_propagate_labels(sx, sn, so, dx, dn, thresh=0.5):
+    sx = np.ascontiguousarray(sx, np.float32); sn = np.ascontiguousarray(sn, np.float32); so = np.ascontiguousarray(so, np.uint32)
+    dx = np.ascontiguousarray(dx, np.float32); dn = np.ascontiguousarray(dn, np.float32)
+    out = np.zeros(len(dx), np.uint32); edge = np.zeros(len(dx), np.uint8)
+    segs_oracle().oracle_propagate_labels(sx.ctypes.data, sn.ctypes.data, so.ctypes.data, len(sx), dx.ctypes.data, dn.ctypes.data, len(dx),
+                                          thresh, out.ctypes.data, edge.ctypes.data)
+    return out, edge.astype(bool)
