@@ -93,6 +93,7 @@ struct scn_tsdf {
   scn_tsdf_detail::Tables tb{};
   uint64_t cap = 0;
   float* dm = nullptr;
+  unsigned* rgbx = nullptr;        // colour of the current batches repacked to one word per pixel (2 parities), allocated on first use
   uint16_t* d_depth[2] = {nullptr, nullptr};     // H2D staging, double buffered
   uint8_t* d_rgb[2] = {nullptr, nullptr};
   uint16_t* h_depth[2] = {nullptr, nullptr};     // pinned bounce buffers (pageable callers)
