@@ -23,8 +23,10 @@
 //       by edges 0..i-1); they run on the host over the device-sorted records.
 // Float arithmetic: explicit round-to-nearest intrinsics, no contraction (-fmad=false), IEEE sqrt/div.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 #include "scan.cuh"
@@ -458,20 +460,19 @@ __global__ void k_compact_edges(const Rec* __restrict__ rec, const unsigned* __r
 // every top-level call and regrown to a single chunk when a call overflowed it.
 struct Arena {
   struct Chunk { char* p; size_t cap; };
-  std::vector<Chunk> chunks; size_t used = 0, total_req = 0; int dev = -1;
+  std::vector<Chunk> chunks; size_t used = 0, total_req = 0, last_total = 0; int dev = -1;
+  void release() { for (Chunk& c : chunks) cudaFree(c.p); chunks.clear(); used = 0; }
   void reset() {
     int d = 0; cudaGetDevice(&d);
-    if (d != dev || chunks.size() > 1) {
-      for (Chunk& c : chunks) cudaFree(c.p);
-      chunks.clear();
-      if (d == dev && total_req) { Chunk c{nullptr, total_req + (total_req >> 3) + (1u << 20)}; if (cudaMalloc(&c.p, c.cap) == cudaSuccess) chunks.push_back(c); }
-      dev = d;
-    }
-    used = 0; total_req = 0;
+    if (d != dev || chunks.size() > 1) { release(); dev = d; }     // a call that overflowed its chunk: start over with one big enough
+    last_total = total_req; used = 0; total_req = 0;
   }
-  // make room for `bytes` more in one chunk (called once per top-level call with an upper bound of its needs)
+  // make room for `bytes` more in one chunk (called once per top-level call, right after reset(), with an upper bound of its
+  // needs); the chunk is kept across calls, so steady-state calls of similar size never touch cudaMalloc
   void reserve(size_t bytes) {
+    bytes = std::max(bytes, last_total + (last_total >> 3));
     if (!chunks.empty() && used + bytes <= chunks.back().cap) return;
+    if (used == 0) release();                                       // nothing live yet: replace rather than accumulate
     Chunk c{nullptr, bytes + (1u << 20)};
     if (cudaMalloc(&c.p, c.cap) != cudaSuccess) { cudaGetLastError(); return; }   // fall back to piecemeal chunks
     chunks.push_back(c); used = 0;
@@ -488,7 +489,7 @@ struct Arena {
 };
 thread_local Arena g_arena;
 struct PinnedBuf { void* p = nullptr; size_t cap = 0; void* get(size_t n) { if (n > cap) { if (p) cudaFreeHost(p); p = nullptr; cap = 0; if (cudaHostAlloc(&p, n + (n >> 3), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; } cap = n + (n >> 3); } return p; } };
-thread_local PinnedBuf g_pinned;
+thread_local PinnedBuf g_pinned, g_pinned_in;
 
 struct DevBuf {
   void* p = nullptr;
@@ -574,17 +575,32 @@ inline void uf_join(UfElt* u, int x, int y) {
   if (u[x].rank > u[y].rank) { u[y].p = x; u[x].size += u[y].size; }
   else { u[x].p = y; u[y].size += u[x].size; if (u[x].rank == u[y].rank) u[y].rank++; }
 }
-constexpr size_t kPrefetch = 24;
+// The replay is bound by dependent cache misses on the forest.  Measured on the GPU box's host (Xeon 8562Y+, 2 M-vertex mesh,
+// 6 M records): plain find + prefetch 24 ahead 103 ms; prefetching the records 48 ahead and walking two parent links of the
+// record 8 ahead (read-only) + full path compression 86 ms.  Path compression changes only parent pointers, never roots,
+// ranks, sizes or thresholds, so the ids are the reference's.
+inline int uf_find_full(UfElt* U, int x) {
+  int y = x; while (y != U[y].p) y = U[y].p;
+  while (U[x].p != y) { const int n = U[x].p; U[x].p = y; x = n; }
+  return y;
+}
+inline void uf_prefetch(const UfElt* U, const Edge12* e, size_t i, size_t nE) {
+  if (i + 48 < nE) { __builtin_prefetch(U + e[i + 48].a); __builtin_prefetch(U + e[i + 48].b); }
+  if (i + 8 < nE) {
+    int y = e[i + 8].a; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y);
+    y = e[i + 8].b; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y);
+  }
+}
 void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<UfElt>& u) {
   u.resize(nV);
   for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; u[i].thr = c; }
   UfElt* U = u.data();
   for (size_t i = 0; i < nE; ++i) {
-    if (i + kPrefetch < nE) { __builtin_prefetch(U + e[i + kPrefetch].a); __builtin_prefetch(U + e[i + kPrefetch].b); }
-    int a = uf_find(U, e[i].a), b = uf_find(U, e[i].b);
+    uf_prefetch(U, e, i, nE);
+    int a = uf_find_full(U, e[i].a), b = uf_find_full(U, e[i].b);
     if (a != b && e[i].w <= U[a].thr && e[i].w <= U[b].thr) {
       uf_join(U, a, b);
-      a = uf_find(U, a);
+      a = uf_find_full(U, a);
       U[a].thr = e[i].w + (c / (float)U[a].size);
     }
   }
@@ -592,16 +608,17 @@ void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<Uf
 void host_small_merge(const Edge12* e, size_t nE, int min_verts, std::vector<UfElt>& u) {
   UfElt* U = u.data();
   for (size_t j = 0; j < nE; ++j) {
-    if (j + kPrefetch < nE) { __builtin_prefetch(U + e[j + kPrefetch].a); __builtin_prefetch(U + e[j + kPrefetch].b); }
-    const int a = uf_find(U, e[j].a), b = uf_find(U, e[j].b);
+    uf_prefetch(U, e, j, nE);
+    const int a = uf_find_full(U, e[j].a), b = uf_find_full(U, e[j].b);
     if (a != b && (U[a].size < min_verts || U[b].size < min_verts)) uf_join(U, a, b);
   }
 }
 
 // Device: drop provable no-op records (see k_pair_first), copy the survivors to pinned host memory.  Returns the
 // pruned, still weight-sorted records in *out (pointer into a cached pinned buffer) and their count.
-int prune_and_download(const Rec* dRec, const unsigned* dTri, const Edge12* dSrc, size_t nE, cudaStream_t st, const Edge12** out, size_t* n_out) {
-  *out = nullptr; *n_out = 0;
+int prune_and_download(const Rec* dRec, const unsigned* dTri, const Edge12* dSrc, size_t nE, cudaStream_t st, const Edge12** out, size_t* n_out,
+                       const Edge12** d_out = nullptr) {
+  *out = nullptr; *n_out = 0; if (d_out) *d_out = nullptr;
   if (!nE) return SCN_OK;
   size_t cap = 1; while (cap < 2 * nE) cap <<= 1;
   DevBuf dK, dM, dKeep, dPos, dOut, dScr;
@@ -622,9 +639,60 @@ int prune_and_download(const Rec* dRec, const unsigned* dTri, const Edge12* dSrc
   CK(cudaMemcpyAsync(h, dOut.p, (size_t)nk * 12, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  *out = (const Edge12*)h; *n_out = nk;
+  *out = (const Edge12*)h; *n_out = nk; if (d_out) *d_out = dOut.as<Edge12>();
   return SCN_OK;
 }
+
+// Small-segment pass (segmentator.cpp:237-243) pre-filter.  After the Kruskal pass an edge whose ends already share a root,
+// or whose two components both have >= segMinVerts vertices, can never act in the second pass (components only merge and
+// sizes only grow), so only the few edges between a small component and a neighbour need the sequential replay.  The forest
+// (parent, size) goes to the device, every vertex resolves its root, the still-resident pruned edge array is filtered and
+// compacted in order, and the survivors come back.
+__global__ void k_uf_roots(const int2* __restrict__ ps, size_t nV, int* __restrict__ root) {
+  const size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  int y = (int)v;
+  for (;;) { const int p = ps[y].x; if (p == y) break; y = p; }
+  root[v] = y;
+}
+__global__ void k_small_keep(const Edge12* __restrict__ e, size_t nK, const int* __restrict__ root, const int2* __restrict__ ps, int min_verts,
+                             unsigned* __restrict__ keep) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= nK) return;
+  const int ra = root[e[j].a], rb = root[e[j].b];
+  keep[j] = (ra != rb && (ps[ra].y < min_verts || ps[rb].y < min_verts)) ? 1u : 0u;
+}
+__global__ void k_compact12(const Edge12* __restrict__ e, size_t nK, const unsigned* __restrict__ keep, const unsigned* __restrict__ pos,
+                            Edge12* __restrict__ out) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j < nK && keep[j]) out[pos[j]] = e[j];
+}
+int filter_small_merge(const Edge12* dE, size_t nK, const std::vector<UfElt>& u, int min_verts, cudaStream_t st, const Edge12** out, size_t* n_out) {
+  const size_t nV = u.size();
+  int2* hps = (int2*)g_pinned_in.get(nV * 8);
+  if (!hps) return scn::fail(SCN_ERR_CUDA, "cudaHostAlloc (forest upload)");
+  for (size_t v = 0; v < nV; ++v) hps[v] = make_int2(u[v].p, u[v].size);
+  DevBuf dPs, dRoot, dKeep, dPos, dOut, dScr;
+  if (dPs.alloc(nV * 8) || dRoot.alloc(nV * 4) || dKeep.alloc(nK * 4) || dPos.alloc((nK + 1) * 4) || dOut.alloc(nK * 12) || dScr.alloc(scn::scan_scratch_elems(nK) * 4))
+    return scn::fail(SCN_ERR_CUDA, "cudaMalloc (small-segment filter workspace)");
+  CK(cudaMemcpyAsync(dPs.p, hps, nV * 8, cudaMemcpyHostToDevice, st));
+  k_uf_roots<<<(unsigned)((nV + 255) / 256), 256, 0, st>>>(dPs.as<int2>(), nV, dRoot.as<int>());
+  const unsigned g = (unsigned)((nK + 255) / 256);
+  k_small_keep<<<g, 256, 0, st>>>(dE, nK, dRoot.as<int>(), dPs.as<int2>(), min_verts, dKeep.as<unsigned>());
+  scn::exclusive_scan_u32(dKeep.as<unsigned>(), dPos.as<unsigned>(), nK, dScr.as<unsigned>(), st);
+  k_compact12<<<g, 256, 0, st>>>(dE, nK, dKeep.as<unsigned>(), dPos.as<unsigned>(), dOut.as<Edge12>());
+  unsigned n2 = 0;
+  CK(cudaMemcpyAsync(&n2, dPos.as<unsigned>() + nK, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  void* h = g_pinned.get((size_t)n2 * 12 + 16);                 // the Kruskal pass is done with the previous contents
+  if (!h) return scn::fail(SCN_ERR_CUDA, "cudaHostAlloc (%u records)", n2);
+  CK(cudaMemcpyAsync(h, dOut.p, (size_t)n2 * 12, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  *out = (const Edge12*)h; *n_out = n2;
+  return SCN_OK;
+}
+constexpr size_t kSmallFilterMin = 200000;      // below this the sequential pass is cheaper than the round trip
 
 struct Timer {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -643,16 +711,41 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   Timer total, lapt;
   g_arena.reset();
   const size_t nE = 3 * nF;
-  g_arena.reserve(80 * nE + 64 * (size_t)nV + (size_t(32) << 20));      // upper bound of every buffer below incl. sort + pruning
-  for (uint64_t i = 0; i < 3 * nF; ++i) if (tri[i] >= nV) return scn::fail(SCN_ERR_FORMAT, "face %llu references vertex %u >= %llu", (unsigned long long)(i / 3), tri[i], (unsigned long long)nV);
+  g_arena.reserve(104 * nE + 80 * (size_t)nV + (size_t(32) << 20));      // upper bound of every buffer below incl. sort + pruning
+  // Inputs are usually pageable: a plain cudaMemcpy of the 72 MB of a 2 M-vertex mesh took ~60 ms.  A few host threads copy
+  // slices into a cached pinned buffer (checking the indices on the way), then one DMA per array moves them.
+  const size_t xyz_bytes = nV * 12, tri_bytes = nF * 12;
+  char* stage = (xyz_bytes + tri_bytes >= (size_t(4) << 20)) ? (char*)g_pinned_in.get(xyz_bytes + tri_bytes) : nullptr;
+  std::atomic<uint64_t> bad{~0ull};
+  if (stage) {
+    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned t) {
+      const size_t x0 = xyz_bytes * t / nt, x1 = xyz_bytes * (t + 1) / nt;
+      memcpy(stage + x0, (const char*)xyz + x0, x1 - x0);
+      const size_t i0 = 3 * nF * t / nt, i1 = 3 * nF * (t + 1) / nt;
+      uint32_t* dst = (uint32_t*)(stage + xyz_bytes);
+      uint32_t mx = 0;
+      for (size_t i = i0; i < i1; ++i) { const uint32_t v = tri[i]; dst[i] = v; mx = v > mx ? v : mx; }
+      if (mx >= nV) for (size_t i = i0; i < i1; ++i) if (tri[i] >= nV) { uint64_t cur = bad.load(); while (i < cur && !bad.compare_exchange_weak(cur, i)) {} break; }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+  } else {
+    for (uint64_t i = 0; i < 3 * nF; ++i) if (tri[i] >= nV) { bad = i; break; }
+  }
+  if (bad.load() != ~0ull) { const uint64_t i = bad.load(); return scn::fail(SCN_ERR_FORMAT, "face %llu references vertex %u >= %llu", (unsigned long long)(i / 3), tri[i], (unsigned long long)nV); }
+  const void* src_xyz = stage ? (const void*)stage : (const void*)xyz;
+  const void* src_tri = stage ? (const void*)(stage + xyz_bytes) : (const void*)tri;
   cudaStream_t st = nullptr;
   DevBuf dXyz, dTri, dFn, dDeg, dOff, dCur, dCsr, dNrm, dRec, dE12, dScr;
   if (dXyz.alloc(nV * 12) || dTri.alloc(nF * 12) || dFn.alloc(nF * 16) || dDeg.alloc((nV + 1) * 4) || dOff.alloc((nV + 2) * 4) ||
       dCur.alloc((nV + 1) * 4) || dCsr.alloc(nE * 4) || dNrm.alloc(nV * 12) || dRec.alloc(nE * 8) || dE12.alloc(nE * 12) ||
       dScr.alloc(scn::scan_scratch_elems(nV + 1) * 4))
     return scn::fail(SCN_ERR_CUDA, "cudaMalloc (segmentator workspace)");
-  CK(cudaMemcpyAsync(dXyz.p, xyz, nV * 12, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dTri.p, tri, nF * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dXyz.p, src_xyz, nV * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dTri.p, src_tri, nF * 12, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(dDeg.p, 0, (nV + 1) * 4, st));
   CK(cudaMemsetAsync(dCur.p, 0, (nV + 1) * 4, st));
   CK(cudaStreamSynchronize(st));
@@ -684,8 +777,8 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
     CK(cudaMemcpy(edges_sorted, dE12.p, nE * 12, cudaMemcpyDeviceToHost));
     lapt.lap();
   }
-  const Edge12* hE = nullptr; size_t nK = 0;
-  rc = prune_and_download(dRec.as<Rec>(), dTri.as<unsigned>(), nullptr, nE, st, &hE, &nK);
+  const Edge12* hE = nullptr; const Edge12* dE = nullptr; size_t nK = 0;
+  rc = prune_and_download(dRec.as<Rec>(), dTri.as<unsigned>(), nullptr, nE, st, &hE, &nK, &dE);
   if (rc) return rc;
   g_timings[6] = lapt.lap();
   std::vector<UfElt> u;
@@ -693,6 +786,7 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   g_timings[4] = lapt.lap();
   if (roots_after_kruskal) for (size_t q = 0; q < nV; ++q) { int y = (int)q; while (y != u[y].p) y = u[y].p; roots_after_kruskal[q] = y; }
   lapt.lap();
+  if (nK >= kSmallFilterMin) { rc = filter_small_merge(dE, nK, u, min_verts, st, &hE, &nK); if (rc) return rc; }
   host_small_merge(hE, nK, min_verts, u);
   g_timings[5] = lapt.lap();
   for (size_t q = 0; q < nV; ++q) seg_out[q] = uf_find(u.data(), (int)q);
