@@ -234,6 +234,29 @@ def sens_bench(n_frames=120):
         for i in range(n_frames):
             s.depth(i)
         out["depth_decode_fps_1thread"] = n_frames / (time.perf_counter() - t0)
+        # the same frames inflated on the GPU, one warp per frame; 8 passes over the file's streams in one launch (960 frames)
+        try:
+            import ctypes as C2
+            import torch
+            from scannet_b200 import sens as _sens
+            from scannet_b200._lib import check as _check, lib as _lib
+            pay = []
+            for i in range(n_frames):
+                cp = C2.c_void_p(); dp = C2.c_void_p(); db = C2.c_uint64()
+                _check(_lib().scn_sens_frame_payload(s._h, C2.c_uint64(i), C2.byref(cp), C2.byref(dp)))
+                _check(_lib().scn_sens_frame_meta(s._h, C2.c_uint64(i), None, None, None, None, C2.byref(db)))
+                pay.append(C2.string_at(dp.value, db.value))
+            reps = 8; streams = pay * reps
+            dout = torch.empty((len(streams), H, W), dtype=torch.int16, device="cuda")
+            _sens.inflate_batch_device(streams[:16], W * H * 2, dout.data_ptr())            # warm-up (staging buffers, module load)
+            _sens.inflate_batch_device(streams, W * H * 2, dout.data_ptr())
+            t0 = time.perf_counter(); _sens.inflate_batch_device(streams, W * H * 2, dout.data_ptr()); dt = time.perf_counter() - t0
+            ok = bool((dout[-1].cpu().numpy().view(np.uint16) == D[-1]).all() and (dout[0].cpu().numpy().view(np.uint16) == D[0]).all())
+            out["depth_decode_gpu"] = {"frames": len(streams), "fps_incl_pack_and_h2d": len(streams) / dt, "identical_to_host_decode": ok,
+                                       "compressed_bytes_per_frame": int(sum(len(b) for b in pay) / len(pay))}
+            del dout
+        except Exception as e:                                                                 # a side measurement must not take the bench line down
+            out["depth_decode_gpu"] = {"error": repr(e)}
         ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_sens.so")
         if os.path.exists(ref_so):
             L = C.CDLL(ref_so); L.ref_sens_open.restype = C.c_void_p; L.ref_sens_open.argtypes = [C.c_char_p]
@@ -250,6 +273,9 @@ def sens_bench(n_frames=120):
         r = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "fuse"), prm, p], capture_output=True, text=True)
         out["fuse_cli_wall_s"] = time.perf_counter() - t0
         out["fuse_cli_stdout"] = [ln for ln in r.stdout.splitlines() if ln.startswith(("integrated", "mesh written"))]
+        r = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "fuse"), prm, p, os.path.join(d, "g.ply")], capture_output=True, text=True,
+                           env=dict(os.environ, SCN_FUSE_DECODE="gpu"))
+        out["fuse_cli_gpu_decode_stdout"] = [ln for ln in r.stdout.splitlines() if ln.startswith(("integrated", "depth decode"))]
     return out
 
 

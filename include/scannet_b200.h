@@ -38,6 +38,14 @@ int  scn_cuda_warmup(void);
 void* scn_host_alloc(size_t bytes);
 void  scn_host_free(void* p);
 void  scn_free(void* p);                      /* frees buffers this library malloc'ed for the caller */
+/* device memory / stream helpers for callers without a CUDA runtime of their own (buffers for scn_sens_decode_depth_device and
+ * scn_tsdf_integrate_device); the copies return when the transfer has completed */
+void* scn_device_alloc(size_t bytes);
+void  scn_device_free(void* p);
+int   scn_stream_create(void** stream_out);          /* non-blocking cudaStream_t */
+void  scn_stream_destroy(void* stream);
+int   scn_memcpy_h2d(void* d_dst, const void* src, size_t bytes, void* stream);
+int   scn_memcpy_d2h(void* dst, const void* d_src, size_t bytes, void* stream);
 
 /* ===================================================================== Segmentator ====
  * Replaces: std::vector<int> segment(const std::string&, float, int)   Segmentator/segmentator.cpp:123
@@ -252,6 +260,19 @@ int  scn_mesh_vertex_normals(const float* xyz, uint64_t n_verts, const uint32_t*
 int  scn_propagate_labels(const float* src_xyz, const float* src_normals, const uint32_t* src_obj, uint64_t n_src,
                           const float* dst_xyz, const float* dst_normals, uint64_t n_dst, float normal_thresh,
                           uint32_t* dst_obj_out);
+/* ------------------------------------------------------------------------------------------------------------------
+ * GPU depth decode: TYPE_ZLIB_USHORT payloads (sensorData.h:703-709) are uploaded compressed and inflated
+ * in device memory, one warp per frame.  d_depth_out: device pointer, n * depth_width * depth_height uint16, frame after
+ * frame — exactly what scn_tsdf_integrate_device consumes.  `stream` is a cudaStream_t (NULL = default stream); the call
+ * returns when the frames are decoded.  Same bytes and the same error cases as scn_sens_frame_depth_u16.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int  scn_sens_decode_depth_device(const scn_sens* s, uint64_t first_frame, uint32_t n, uint16_t* d_depth_out, void* stream);
+/* the same for caller-supplied zlib streams: src[i] / src_bytes[i] on the host, each must inflate to >= frame_bytes */
+int  scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_bytes, uint32_t n, uint64_t frame_bytes, void* d_out,
+                              void* stream);
+/* host build of the same decoder source (one lane): used by the CPU test-suite; not a product path */
+int  scn_inflate_host(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* produced);
+
 /* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract. */
 int  scn_fuse_main(int argc, const char** argv);
 

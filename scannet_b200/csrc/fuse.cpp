@@ -33,7 +33,7 @@ void build_color_lut(const scn_sens_info_t& in, std::vector<int32_t>& lut) {
   }
 }
 
-void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vector<int32_t>& lut, bool use_color, uint64_t f0, uint32_t n, Chunk& c, unsigned threads) {
+void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vector<int32_t>& lut, bool use_color, bool want_depth, uint64_t f0, uint32_t n, Chunk& c, unsigned threads) {
   const size_t px = (size_t)in.depth_width * in.depth_height;
   c.n = n; c.rc = 0; c.poses.assign((size_t)n * 16, 0.f);
   std::atomic<uint32_t> next{0}; std::atomic<int> rc{0};
@@ -44,7 +44,7 @@ void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vecto
       if (i >= n || rc.load()) break;
       scn_sens_frame_meta(s, f0 + i, &c.poses[(size_t)i * 16], nullptr, nullptr, nullptr, nullptr);
       if (c.poses[(size_t)i * 16] == -INFINITY) continue;                        // skipped by the integrator anyway
-      int r = scn_sens_frame_depth_u16(s, f0 + i, c.depth + (size_t)i * px);
+      int r = want_depth ? scn_sens_frame_depth_u16(s, f0 + i, c.depth + (size_t)i * px) : 0;
       if (!r && use_color) {
         r = scn_sens_frame_color_rgb8(s, f0 + i, col.data());
         if (!r) { uint8_t* o = c.rgb + (size_t)i * px * 3;
@@ -98,18 +98,52 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   for (Chunk& c : ch) { c.depth = (uint16_t*)scn_host_alloc(CH * px * 2); c.rgb = use_color ? (uint8_t*)scn_host_alloc(CH * px * 3) : nullptr;
     if (!c.depth || (use_color && !c.rgb)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; } }
   std::vector<int32_t> lut; if (use_color) build_color_lut(in, lut);
+  // Depth decode.  Default: the host pool.  SCN_FUSE_DECODE=gpu: the compressed depth payloads of up to 8192 frames at a time
+  // are uploaded and inflated in HBM in ONE launch (one warp per frame — a deflate stream is sequential, so the GPU only pays
+  // off with thousands of frames in flight; see csrc/inflate.cu) while the host pool decodes the colour of the same frames
+  // into a second HBM-resident array; the super-chunk is then fused from device memory.
+  const char* dec_env = getenv("SCN_FUSE_DECODE");
+  const bool gpu_decode = in.depth_compression == 1 && dec_env && !strcmp(dec_env, "gpu");
+  printf("depth decode: %s\n", gpu_decode ? "GPU inflate (one warp per frame)" : "host thread pool");
   const auto t0 = std::chrono::steady_clock::now();
   int rc = 0; uint64_t f = 0; int cur = 0;
-  if (in.n_frames) decode_chunk(s, in, lut, use_color, 0, (uint32_t)std::min<uint64_t>(CH, in.n_frames), ch[0], threads);
-  while (f < in.n_frames && !rc) {
-    Chunk& c = ch[cur];
-    if (c.rc) { fprintf(stderr, "%s\n", c.err.c_str()); rc = 1; break; }
-    // the GPU consumes chunk `cur` asynchronously while the host decodes the next one into the other buffer
-    if (scn_tsdf_integrate_batch(vol, c.n, c.depth, c.rgb, c.poses.data(), in.depth_intrinsic)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }
-    f += c.n;
-    if (f < in.n_frames) decode_chunk(s, in, lut, use_color, f, (uint32_t)std::min<uint64_t>(CH, in.n_frames - f), ch[cur ^ 1], threads);
-    if (scn_tsdf_sync(vol)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }      // chunk `cur` may be overwritten next round
-    cur ^= 1;
+  if (gpu_decode) {
+    const uint64_t SUPER = std::min<uint64_t>(8192, in.n_frames);
+    uint16_t* d_depth = (uint16_t*)scn_device_alloc((size_t)SUPER * px * 2);
+    uint8_t* d_rgb = use_color ? (uint8_t*)scn_device_alloc((size_t)SUPER * px * 3) : nullptr;
+    void* dec_stream = nullptr; void* up_stream = nullptr;
+    if (!d_depth || (use_color && !d_rgb) || scn_stream_create(&dec_stream) || scn_stream_create(&up_stream)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+    std::vector<float> poses;
+    while (f < in.n_frames && !rc) {
+      const uint32_t n = (uint32_t)std::min<uint64_t>(SUPER, in.n_frames - f);
+      int dec_rc = 0; std::string dec_err;
+      std::thread dec([&]() { dec_rc = scn_sens_decode_depth_device(s, f, n, d_depth, dec_stream); if (dec_rc) dec_err = scn_last_error(); });
+      poses.assign((size_t)n * 16, 0.f);
+      for (uint32_t c0 = 0; c0 < n && !rc; c0 += CH) {                       // colour (and poses) of this super-chunk, CH frames at a time
+        const uint32_t cn = std::min<uint32_t>(CH, n - c0);
+        decode_chunk(s, in, lut, use_color, false, f + c0, cn, ch[0], threads);
+        if (ch[0].rc) { fprintf(stderr, "%s\n", ch[0].err.c_str()); rc = 1; break; }
+        memcpy(&poses[(size_t)c0 * 16], ch[0].poses.data(), (size_t)cn * 64);
+        if (use_color && scn_memcpy_h2d(d_rgb + (size_t)c0 * px * 3, ch[0].rgb, (size_t)cn * px * 3, up_stream)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+      }
+      dec.join();
+      if (dec_rc) { fprintf(stderr, "%s\n", dec_err.c_str()); rc = 1; }
+      if (!rc && (scn_tsdf_integrate_device(vol, n, d_depth, d_rgb, poses.data(), in.depth_intrinsic) || scn_tsdf_sync(vol))) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+      f += n;
+    }
+    scn_device_free(d_depth); scn_device_free(d_rgb); scn_stream_destroy(dec_stream); scn_stream_destroy(up_stream);
+  } else {
+    if (in.n_frames) decode_chunk(s, in, lut, use_color, true, 0, (uint32_t)std::min<uint64_t>(CH, in.n_frames), ch[0], threads);
+    while (f < in.n_frames && !rc) {
+      Chunk& c = ch[cur];
+      if (c.rc) { fprintf(stderr, "%s\n", c.err.c_str()); rc = 1; break; }
+      // the GPU consumes chunk `cur` asynchronously while the host decodes the next one into the other buffer
+      if (scn_tsdf_integrate_batch(vol, c.n, c.depth, c.rgb, c.poses.data(), in.depth_intrinsic)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }
+      f += c.n;
+      if (f < in.n_frames) decode_chunk(s, in, lut, use_color, true, f, (uint32_t)std::min<uint64_t>(CH, in.n_frames - f), ch[cur ^ 1], threads);
+      if (scn_tsdf_sync(vol)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }      // chunk `cur` may be overwritten next round
+      cur ^= 1;
+    }
   }
   const double fuse_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (!rc) {
@@ -123,6 +157,7 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
     scn_free(xyz); scn_free(rgb); scn_free(tri);
   }
   for (Chunk& c : ch) { scn_host_free(c.depth); scn_host_free(c.rgb); }
+
   scn_tsdf_destroy(vol); scn_sens_close(s);
   return rc;
 }

@@ -1,0 +1,366 @@
+// Depth decode on the GPU: the TYPE_ZLIB_USHORT payloads of a .sens stream
+// (SensReader/c++/src/sensorData.h:703-709, stbi_zlib_decode_malloc) are uploaded COMPRESSED and inflated in HBM, so raw
+// depth never crosses PCIe and never touches a host core.
+//
+// A deflate stream has no internal synchronisation points, so the parallelism is across frames: ONE WARP PER FRAME.
+// All 32 lanes run the same bit reader and Huffman decoder redundantly (same addresses -> broadcast loads, no divergence,
+// no shuffles), lane 0 stores literals, and LZ77 matches are copied by the whole warp: byte i of a match is
+// out[o - dist + (i mod dist)], which only reads bytes that existed before the match, so the 32 lanes are independent
+// even when the match overlaps itself (runs of zeros: dist = 2, len = 258).  With hundreds of frames in flight every SM
+// sub-partition holds a few such warps; the 180 GB of HBM hold a whole scan decoded (5,578 frames = 3.4 GB).
+// Fixed-Huffman blocks (what stb's compressor — the one the ScanNet tools use — emits) are decoded arithmetically from a
+// bit-reversed 9-bit peek; dynamic blocks use canonical first-code/offset tables (16 compares at most) kept in shared
+// memory; stored blocks are copied.  The same source compiles for the host (lanes = 1) so the decoder is unit-tested
+// on the CPU against zlib streams of every block type.
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "scn_common.h"
+
+#define SCN_HD __host__ __device__ __forceinline__
+
+namespace {
+
+struct HuffTab {                     // canonical Huffman code, lengths 1..15
+  uint16_t count[16];                // codes per length
+  uint16_t first[16];                // first code of each length
+  uint16_t offs[16];                 // index of that code's symbol in sym[]
+  uint16_t sym[288];
+};
+struct InflateScratch { HuffTab lit, dist; uint8_t lens[320]; };
+
+struct BitIn { const uint8_t* p; size_t n, pos; uint64_t bb; int bc; int over; };
+
+// Guarantees more than 32 valid bits (every decode step needs at most 32: a length code + extra bits is 20, a distance
+// code + extra bits 28, a stored-block header 32).  One aligned 32-bit load per four input bytes: the dependent chain of
+// a single warp is what bounds the kernel, so fewer, wider loads matter.  Past the end the buffer is zero-filled and the
+// shortfall remembered.
+SCN_HD void bi_refill(BitIn& b) {
+  while (b.bc <= 32) {
+    if ((((size_t)(b.p + b.pos)) & 3) == 0 && b.pos + 4 <= b.n) { b.bb |= (uint64_t)(*(const uint32_t*)(b.p + b.pos)) << b.bc; b.pos += 4; b.bc += 32; }
+    else if (b.pos < b.n) { b.bb |= (uint64_t)b.p[b.pos++] << b.bc; b.bc += 8; }
+    else { b.over += 8; b.bc += 8; }
+  }
+}
+SCN_HD unsigned bi_peek(const BitIn& b, int n) { return (unsigned)(b.bb & ((1ull << n) - 1ull)); }
+SCN_HD void bi_drop(BitIn& b, int n) { b.bb >>= n; b.bc -= n; }
+SCN_HD unsigned bi_get(BitIn& b, int n) { const unsigned v = bi_peek(b, n); bi_drop(b, n); return v; }
+SCN_HD bool bi_overrun(const BitIn& b) { return b.over > b.bc; }                        // consumed bits that were never in the input
+
+SCN_HD unsigned rev_bits(unsigned v, int n) {
+#ifdef __CUDA_ARCH__
+  return __brev(v) >> (32 - n);
+#else
+  unsigned r = 0; for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; } return r;
+#endif
+}
+
+// RFC 1951 3.2.5 base values / extra bits, packed as (base << 4 | extra)
+SCN_HD unsigned len_code(unsigned i) {
+  const unsigned t[29] = {3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 0, 6 << 4 | 0, 7 << 4 | 0, 8 << 4 | 0, 9 << 4 | 0, 10 << 4 | 0, 11 << 4 | 1, 13 << 4 | 1,
+                          15 << 4 | 1, 17 << 4 | 1, 19 << 4 | 2, 23 << 4 | 2, 27 << 4 | 2, 31 << 4 | 2, 35 << 4 | 3, 43 << 4 | 3, 51 << 4 | 3, 59 << 4 | 3,
+                          67 << 4 | 4, 83 << 4 | 4, 99 << 4 | 4, 115 << 4 | 4, 131 << 4 | 5, 163 << 4 | 5, 195 << 4 | 5, 227 << 4 | 5, 258 << 4 | 0};
+  return t[i];
+}
+SCN_HD unsigned dist_code(unsigned i) {
+  const unsigned t[30] = {1 << 4 | 0, 2 << 4 | 0, 3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 1, 7 << 4 | 1, 9 << 4 | 2, 13 << 4 | 2, 17 << 4 | 3, 25 << 4 | 3,
+                          33 << 4 | 4, 49 << 4 | 4, 65 << 4 | 5, 97 << 4 | 5, 129 << 4 | 6, 193 << 4 | 6, 257 << 4 | 7, 385 << 4 | 7, 513 << 4 | 8, 769 << 4 | 8,
+                          1025 << 4 | 9, 1537 << 4 | 9, 2049 << 4 | 10, 3073 << 4 | 10, 4097 << 4 | 11, 6145 << 4 | 11, 8193 << 4 | 12, 12289 << 4 | 12,
+                          16385 << 4 | 13, 24577 << 4 | 13};
+  return t[i];
+}
+
+// canonical code from code lengths; returns false for an over-subscribed set (incomplete sets are allowed, as in zlib for
+// a single distance code)
+SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n) {
+  for (int i = 0; i < 16; ++i) h.count[i] = 0;
+  for (int i = 0; i < n; ++i) h.count[lens[i]]++;
+  h.count[0] = 0;
+  int left = 1; unsigned code = 0, off = 0;
+  for (int l = 1; l < 16; ++l) {
+    left = (left << 1) - (int)h.count[l];
+    if (left < 0) return false;
+    code = (code + h.count[l - 1]) << 1;
+    h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += h.count[l];
+  }
+  uint16_t next[16];
+  for (int l = 1; l < 16; ++l) next[l] = h.offs[l];
+  for (int i = 0; i < n; ++i) if (lens[i]) h.sym[next[lens[i]]++] = (uint16_t)i;
+  return true;
+}
+// decode one symbol (caller guarantees >= 15 bits in the buffer: bi_refill leaves > 32); -1 = invalid code
+SCN_HD int huff_decode(BitIn& b, const HuffTab& h) {
+  const unsigned r = rev_bits(bi_peek(b, 15), 15);
+  for (int l = 1; l < 16; ++l) {
+    const unsigned c = (r >> (15 - l)) - h.first[l];
+    if (c < h.count[l]) { bi_drop(b, l); return h.sym[h.offs[l] + c]; }
+  }
+  return -1;
+}
+// fixed code of RFC 1951 3.2.6 without tables
+SCN_HD int fixed_lit_decode(BitIn& b) {
+  const unsigned r = rev_bits(bi_peek(b, 9), 9);
+  const unsigned t7 = r >> 2, t8 = r >> 1;
+  if (t7 <= 23u) { bi_drop(b, 7); return 256 + (int)t7; }
+  if (t8 >= 0x30u && t8 <= 0xBFu) { bi_drop(b, 8); return (int)t8 - 0x30; }
+  if (t8 >= 0xC0u && t8 <= 0xC7u) { bi_drop(b, 8); return 280 + (int)t8 - 0xC0; }
+  bi_drop(b, 9); return 144 + (int)r - 0x190;
+}
+
+enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_BAD_DIST = 4, INF_OUT_FULL = 5, INF_TRUNCATED = 6 };
+
+template <int LANES>
+SCN_HD void lanes_sync() {
+#ifdef __CUDA_ARCH__
+  if (LANES > 1) __syncwarp();
+#endif
+}
+
+// Inflates one zlib stream.  Every lane executes this with identical arguments except `lane`; the output is written
+// cooperatively.  Returns INF_* and the number of bytes produced.
+template <int LANES>
+SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, int lane, InflateScratch* scr, size_t* produced) {
+  *produced = 0;
+  if (n < 2) return INF_BAD_HEADER;
+  const unsigned cmf = in[0], flg = in[1];
+  if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return INF_BAD_HEADER;     // RFC 1950; preset dictionaries are not used
+  BitIn b{in, n, 2, 0ull, 0, 0};
+  size_t o = 0;
+  for (;;) {
+    bi_refill(b);
+    const unsigned last = bi_get(b, 1), type = bi_get(b, 2);
+    if (type == 0) {                                             // stored
+      bi_drop(b, b.bc & 7);
+      bi_refill(b);
+      const unsigned len = bi_get(b, 16), nlen = bi_get(b, 16);
+      if ((len ^ 0xFFFFu) != nlen || bi_overrun(b)) return INF_BAD_BLOCK;
+      // the bytes still in the bit buffer come first, then straight from the input
+      const size_t src0 = b.pos - (size_t)((b.bc - b.over) / 8);
+      if (src0 + len > n) return INF_TRUNCATED;
+      const size_t take = o + len > cap ? cap - o : (size_t)len;
+      for (size_t i = (size_t)lane; i < take; i += LANES) out[o + i] = in[src0 + i];
+      o += take;
+      if (take < len) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
+      b.pos = src0 + len; b.bb = 0; b.bc = 0; b.over = 0;
+    } else if (type == 1 || type == 2) {
+      if (type == 2) {
+        bi_refill(b);
+        const int hlit = (int)bi_get(b, 5) + 257, hdist = (int)bi_get(b, 5) + 1, hclen = (int)bi_get(b, 4) + 4;
+        if (hlit > 286 || hdist > 30) return INF_BAD_BLOCK;
+        const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        uint8_t cl[19];
+        for (int i = 0; i < 19; ++i) cl[i] = 0;
+        for (int i = 0; i < hclen; ++i) { bi_refill(b); cl[order[i]] = (uint8_t)bi_get(b, 3); }
+        lanes_sync<LANES>();                                      // previous block's tables are dead for every lane
+        if (!huff_build(scr->lit, cl, 19)) return INF_BAD_BLOCK;  // code-length code lives in the lit table for a moment
+        lanes_sync<LANES>();
+        int idx = 0;
+        uint8_t* lens = scr->lens;
+        while (idx < hlit + hdist) {
+          bi_refill(b);
+          const int s = huff_decode(b, scr->lit);
+          if (s < 0) return INF_BAD_CODE;
+          if (s < 16) { lens[idx++] = (uint8_t)s; continue; }
+          int rep; uint8_t v = 0;
+          if (s == 16) { if (idx == 0) return INF_BAD_BLOCK; v = lens[idx - 1]; rep = 3 + (int)bi_get(b, 2); }
+          else if (s == 17) rep = 3 + (int)bi_get(b, 3);
+          else rep = 11 + (int)bi_get(b, 7);
+          if (idx + rep > hlit + hdist) return INF_BAD_BLOCK;
+          while (rep--) lens[idx++] = v;
+        }
+        if (lens[256] == 0) return INF_BAD_BLOCK;
+        lanes_sync<LANES>();
+        if (!huff_build(scr->lit, lens, hlit) || !huff_build(scr->dist, lens + hlit, hdist)) return INF_BAD_BLOCK;
+        lanes_sync<LANES>();
+      }
+      for (;;) {
+        bi_refill(b);
+        const int s = type == 1 ? fixed_lit_decode(b) : huff_decode(b, scr->lit);
+        if (s < 0) return INF_BAD_CODE;
+        if (s < 256) {
+          if (o >= cap) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
+          if (lane == 0) out[o] = (uint8_t)s;
+          ++o;
+          continue;
+        }
+        if (s == 256) break;
+        if (s > 285) return INF_BAD_CODE;
+        const unsigned lc = len_code((unsigned)s - 257u);
+        unsigned len = (lc >> 4) + bi_get(b, (int)(lc & 15u));
+        bi_refill(b);
+        int ds;
+        if (type == 1) ds = (int)rev_bits(bi_get(b, 5), 5); else ds = huff_decode(b, scr->dist);
+        if (ds < 0 || ds > 29) return INF_BAD_CODE;
+        const unsigned dc = dist_code((unsigned)ds);
+        const unsigned dist = (dc >> 4) + bi_get(b, (int)(dc & 15u));
+        if (bi_overrun(b)) return INF_TRUNCATED;
+        if (dist > o) return INF_BAD_DIST;
+        const bool full = o + len > cap;
+        if (full) len = (unsigned)(cap - o);                      // the caller's frame is complete: write what fits and stop
+        lanes_sync<LANES>();                                      // earlier literals / matches are visible to every lane
+        const uint8_t* src = out + (o - dist);
+        uint8_t* dst = out + o;
+        if (dist >= len) { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i]; }
+        else if ((dist & (dist - 1u)) == 0u) { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i & (dist - 1u)]; }
+        else { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i % dist]; }
+        o += len;
+        if (full) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
+      }
+      if (bi_overrun(b)) return INF_TRUNCATED;
+    } else return INF_BAD_BLOCK;
+    if (last) break;
+  }
+  lanes_sync<LANES>();
+  *produced = o;
+  return INF_OK;                                                  // the Adler-32 trailer is not checked (stb_image does not either)
+}
+
+// one warp per stream
+__global__ void __launch_bounds__(32) k_inflate(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ in_off, uint8_t* out,
+                                                  size_t out_stride, size_t out_cap, unsigned n, int* __restrict__ status,
+                                                  unsigned long long* __restrict__ produced) {
+  __shared__ InflateScratch scr;
+  const unsigned s = blockIdx.x;
+  if (s >= n) return;
+  size_t got = 0;
+  const int rc = inflate_zlib<32>(in + in_off[s], (size_t)(in_off[s + 1] - in_off[s]), out + (size_t)s * out_stride, out_cap, (int)threadIdx.x, &scr, &got);
+  if (threadIdx.x == 0) { status[s] = rc; produced[s] = got; }
+}
+
+const char* inf_msg(int rc) {
+  switch (rc) {
+    case INF_BAD_HEADER: return "bad zlib header"; case INF_BAD_BLOCK: return "bad deflate block"; case INF_BAD_CODE: return "invalid Huffman code";
+    case INF_BAD_DIST: return "match distance before start of output"; case INF_OUT_FULL: return "stream longer than the frame"; case INF_TRUNCATED: return "truncated stream";
+    default: return "ok";
+  }
+}
+
+// cached staging, one per calling thread: two 64 MB pinned slices (cudaHostAlloc costs ~0.2 ms per MB, so the pinned part is
+// bounded and reused), a device buffer for the packed streams, per-stream offsets / status / produced counts
+constexpr size_t kSlice = size_t(64) << 20;
+struct InflateStage {
+  uint8_t* h[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+  uint8_t* d = nullptr; size_t cap = 0;
+  unsigned long long* d_off = nullptr; int* d_status = nullptr; unsigned long long* d_prod = nullptr; size_t ncap = 0;
+  void release() {
+    for (int i = 0; i < 2; ++i) { if (h[i]) cudaFreeHost(h[i]); h[i] = nullptr; if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    cudaFree(d); cudaFree(d_off); cudaFree(d_status); cudaFree(d_prod); d = nullptr; d_off = d_prod = nullptr; d_status = nullptr; cap = ncap = 0;
+  }
+  bool ensure(size_t bytes, size_t n) {
+    for (int i = 0; i < 2; ++i) if (!h[i]) {
+      if (cudaHostAlloc((void**)&h[i], kSlice, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+    }
+    if (bytes > cap) {
+      cudaFree(d); d = nullptr; cap = 0;
+      const size_t want = bytes + (bytes >> 2) + 4096;
+      if (cudaMalloc((void**)&d, want) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+      cap = want;
+    }
+    if (n > ncap) {
+      cudaFree(d_off); cudaFree(d_status); cudaFree(d_prod); d_off = d_prod = nullptr; d_status = nullptr; ncap = 0;
+      const size_t want = n + (n >> 2) + 64;
+      if (cudaMalloc((void**)&d_off, (want + 1) * 8) != cudaSuccess || cudaMalloc((void**)&d_status, want * 4) != cudaSuccess || cudaMalloc((void**)&d_prod, want * 8) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+      ncap = want;
+    }
+    return true;
+  }
+};
+thread_local InflateStage g_stage;
+
+}  // namespace
+
+extern "C" {
+
+// Host build of the same decoder (lanes = 1): unit-test hook for the CPU suite.
+int scn_inflate_host(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* produced) {
+  if (!src || !out || !produced) return scn::fail(SCN_ERR_ARG, "null argument");
+  std::vector<InflateScratch> scr(1);
+  const int rc = inflate_zlib<1>(src, n, out, cap, 0, scr.data(), produced);
+  return rc == INF_OK ? SCN_OK : scn::fail(SCN_ERR_FORMAT, "inflate: %s", inf_msg(rc));
+}
+
+// n zlib streams (host pointers) -> n frames of `frame_bytes` each at d_out (device).  Streams are packed back to back
+// (16-byte aligned starts) through two pinned 64 MB slices filled by a few host threads and uploaded while the next slice
+// is being filled, then inflated by one warp each in a single launch.  Every stream must produce at least frame_bytes (the
+// first frame_bytes are kept, as the host path does).  `stream` = cudaStream_t (0 = default); returns after the kernel
+// has completed.
+int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_bytes, uint32_t n, uint64_t frame_bytes, void* d_out, void* stream) {
+  if (!n) return SCN_OK;
+  if (!src || !src_bytes || !d_out) return scn::fail(SCN_ERR_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<unsigned long long> off((size_t)n + 1);
+  size_t tot = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (src_bytes[i] && !src[i]) return scn::fail(SCN_ERR_ARG, "null stream %u", i);
+    if (src_bytes[i] + 16 > kSlice) return scn::fail(SCN_ERR_ARG, "stream %u: %llu bytes is larger than a staging slice", i, (unsigned long long)src_bytes[i]);
+    off[i] = tot; tot += ((size_t)src_bytes[i] + 15) & ~size_t(15);
+  }
+  off[n] = tot;
+  InflateStage& g = g_stage;
+  if (!g.ensure(tot + 16, n)) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: allocation of %zu staging bytes failed", tot);
+  cudaError_t e = cudaMemcpyAsync(g.d_off, off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st);
+  const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  int slot = 0; bool used[2] = {false, false};
+  for (uint32_t i0 = 0; i0 < n && e == cudaSuccess;) {
+    uint32_t i1 = i0; while (i1 < n && off[i1 + 1] - off[i0] <= kSlice) ++i1;               // streams [i0, i1) fit one slice
+    if (used[slot]) e = cudaEventSynchronize(g.ev[slot]);                                   // its previous upload has left the pinned slice
+    if (e != cudaSuccess) break;
+    uint8_t* hs = g.h[slot]; const size_t base = off[i0];
+    auto fill = [&](unsigned t) {
+      for (uint32_t i = i0 + t; i < i1; i += nt) {
+        if (src_bytes[i]) memcpy(hs + (off[i] - base), src[i], (size_t)src_bytes[i]);
+        memset(hs + (off[i] - base) + src_bytes[i], 0, (size_t)(off[i + 1] - off[i] - src_bytes[i]));   // padding is never decoded, but keep it defined
+      }
+    };
+    if (i1 - i0 >= 4 * nt && nt > 1) { std::vector<std::thread> pool; for (unsigned t = 1; t < nt; ++t) pool.emplace_back(fill, t); fill(0); for (auto& th : pool) th.join(); }
+    else for (unsigned t = 0; t < nt; ++t) fill(t);
+    e = cudaMemcpyAsync(g.d + base, hs, (size_t)(off[i1] - base), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(g.ev[slot], st);
+    used[slot] = true; slot ^= 1; i0 = i1;
+  }
+  std::vector<int> status(n); std::vector<unsigned long long> prod(n);
+  if (e == cudaSuccess) {
+    k_inflate<<<n, 32, 0, st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    e = cudaMemcpyAsync(status.data(), g.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(prod.data(), g.d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: %s", cudaGetErrorString(e));
+  for (uint32_t i = 0; i < n; ++i) {
+    if (status[i] != INF_OK && status[i] != INF_OUT_FULL) return scn::fail(SCN_ERR_FORMAT, "frame %u: corrupt zlib depth stream (%s)", i, inf_msg(status[i]));
+    if (prod[i] < frame_bytes) return scn::fail(SCN_ERR_FORMAT, "frame %u: depth stream holds %llu bytes, need %llu", i, prod[i], (unsigned long long)frame_bytes);
+  }
+  return SCN_OK;
+}
+
+// Frames [first, first+n) of an open .sens stream decoded straight into device memory (u16 depth, row-major, frame after
+// frame).  TYPE_ZLIB_USHORT goes through the GPU inflate; TYPE_RAW_USHORT is a plain upload.
+int scn_sens_decode_depth_device(const scn_sens* s, uint64_t first, uint32_t n, uint16_t* d_depth_out, void* stream) {
+  if (!s || (!d_depth_out && n)) return scn::fail(SCN_ERR_ARG, "null argument");
+  scn_sens_info_t info;
+  if (scn_sens_info(s, &info)) return SCN_ERR_ARG;
+  if (first + n > info.n_frames) return scn::fail(SCN_ERR_ARG, "out of bounds");
+  const uint64_t fb = (uint64_t)info.depth_width * info.depth_height * 2;
+  if (info.depth_compression == 2) return scn::fail(SCN_ERR_UNSUPPORTED, "need UPLINK_COMPRESSION");
+  if (info.depth_compression != 0 && info.depth_compression != 1) return scn::fail(SCN_ERR_FORMAT, "invalid type");
+  std::vector<const uint8_t*> src(n); std::vector<uint64_t> len(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint8_t* c = nullptr; const uint8_t* d = nullptr; uint64_t db = 0;
+    if (scn_sens_frame_payload(s, first + i, &c, &d) || scn_sens_frame_meta(s, first + i, nullptr, nullptr, nullptr, nullptr, &db)) return SCN_ERR_ARG;
+    src[i] = d; len[i] = db;
+  }
+  if (info.depth_compression == 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (len[i] < fb) return scn::fail(SCN_ERR_FORMAT, "invalid data");
+      SCN_CUDA_TRY(cudaMemcpyAsync((uint8_t*)d_depth_out + (size_t)i * fb, src[i], fb, cudaMemcpyHostToDevice, st));
+    }
+    SCN_CUDA_TRY(cudaStreamSynchronize(st));
+    return SCN_OK;
+  }
+  return scn_inflate_batch_device(src.data(), len.data(), n, fb, d_depth_out, stream);
+}
+
+}  // extern "C"

@@ -46,6 +46,37 @@ void* scn_host_alloc(size_t bytes) {
 void scn_host_free(void* p) { if (p) cudaFreeHost(p); }
 void scn_free(void* p) { free(p); }
 
+// Device-memory helpers for callers that have no CUDA runtime of their own (the CLIs are plain C++): buffers for
+// scn_sens_decode_depth_device / scn_tsdf_integrate_device, a non-blocking stream, a synchronous upload.
+void* scn_device_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); scn::fail(SCN_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+void scn_device_free(void* p) { if (p) cudaFree(p); }
+int scn_stream_create(void** out) {
+  if (!out) return scn::fail(SCN_ERR_ARG, "null argument");
+  cudaStream_t s = nullptr;
+  SCN_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *out = (void*)s;
+  return SCN_OK;
+}
+void scn_stream_destroy(void* s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int scn_memcpy_h2d(void* d_dst, const void* src, size_t bytes, void* stream) {
+  if (!bytes) return SCN_OK;
+  if (!d_dst || !src) return scn::fail(SCN_ERR_ARG, "null argument");
+  SCN_CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  SCN_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return SCN_OK;
+}
+int scn_memcpy_d2h(void* dst, const void* d_src, size_t bytes, void* stream) {
+  if (!bytes) return SCN_OK;
+  if (!dst || !d_src) return scn::fail(SCN_ERR_ARG, "null argument");
+  SCN_CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SCN_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return SCN_OK;
+}
+
 // Creates the CUDA context (≈0.3 s on a cold process) — the CLIs call it on a helper thread while they read their input file.
 int scn_cuda_warmup(void) { return cudaFree(0) == cudaSuccess ? SCN_OK : scn::fail(SCN_ERR_CUDA, "no usable CUDA device"); }
 

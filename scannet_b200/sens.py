@@ -67,6 +67,10 @@ class SensFile:
         check(_L().scn_sens_frame_depth_u16(self._h, C.c_uint64(i), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def decode_depth_device(self, first: int, n: int, d_out_ptr: int, stream: int = 0):
+        """Frames [first, first+n) inflated on the GPU straight into device memory at `d_out_ptr` (n*H*W uint16)."""
+        check(_L().scn_sens_decode_depth_device(self._h, C.c_uint64(first), C.c_uint32(n), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
     def color(self, i: int) -> np.ndarray:
         out = np.zeros((self.info.color_height, self.info.color_width, 3), np.uint8)
         check(_L().scn_sens_frame_color_rgb8(self._h, C.c_uint64(i), out.ctypes.data_as(C.c_void_p)))
@@ -97,3 +101,19 @@ class SensFile:
         buf = C.create_string_buffer(4096)
         check(_L().scn_sens_describe(self._h, buf, C.c_uint64(4096)))
         return buf.value.decode()
+
+
+def inflate_batch_device(streams, frame_bytes: int, d_out_ptr: int, stream: int = 0):
+    """zlib streams (bytes objects) -> frames of `frame_bytes` at device pointer `d_out_ptr`, one warp per stream."""
+    n = len(streams)
+    bufs = [np.frombuffer(b, np.uint8) if len(b) else np.zeros(1, np.uint8) for b in streams]
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+    lens = (C.c_uint64 * max(n, 1))(*[len(b) for b in streams])
+    check(_L().scn_inflate_batch_device(ptrs, lens, C.c_uint32(n), C.c_uint64(frame_bytes), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+
+def inflate_host(data: bytes, cap: int) -> bytes:
+    """Host build of the GPU decoder source (test hook)."""
+    out = np.zeros(max(cap, 1), np.uint8); n = C.c_size_t()
+    check(_L().scn_inflate_host(data, C.c_size_t(len(data)), out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n)))
+    return out[: n.value].tobytes()

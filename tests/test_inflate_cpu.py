@@ -1,0 +1,58 @@
+"""CPU: the GPU depth decoder's source (scannet_b200/csrc/inflate.cu) compiled for the host with one lane, against zlib
+streams of every deflate block type.  The reference inflates with stb_image's zlib decoder (sensorData.h:703-709); any
+conforming inflate yields the same bytes, so zlib is the ground truth here."""
+import zlib
+
+import numpy as np
+import pytest
+
+from scannet_b200 import sens
+from scannet_b200._lib import ScnError
+
+
+def payloads():
+    rng = np.random.default_rng(0)
+    depth = (rng.integers(500, 4000, (120, 160)) // 8 * 8).astype("<u2"); depth[rng.random(depth.shape) < 0.1] = 0; depth[:30] = 0
+    return {"depth": depth.tobytes(), "empty": b"", "one": b"a", "zeros": bytes(100000), "noise": rng.integers(0, 256, 70000).astype(np.uint8).tobytes(),
+            "period3": b"abcabcabcabc" * 1000 + b"xyz", "period7": bytes(range(7)) * 5000}
+
+
+def encoders():
+    def z(level): return lambda raw: zlib.compress(raw, level)
+    def strat(st, wbits=15, level=6):
+        def f(raw):
+            co = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, st); return co.compress(raw) + co.flush()
+        return f
+    def multi(raw):                                     # several blocks of different types in one stream
+        co = zlib.compressobj(6); out = b""
+        for i in range(0, len(raw), 10000):
+            out += co.compress(raw[i:i + 10000]) + co.flush(zlib.Z_FULL_FLUSH if (i // 10000) % 2 else zlib.Z_SYNC_FLUSH)
+        return out + co.flush()
+    return {"stored": z(0), "fast": z(1), "default": z(6), "best": z(9), "fixed": strat(zlib.Z_FIXED), "huffman_only": strat(zlib.Z_HUFFMAN_ONLY),
+            "window512": strat(zlib.Z_DEFAULT_STRATEGY, 9, 9), "rle": strat(zlib.Z_RLE), "multi_block": multi}
+
+
+@pytest.mark.parametrize("enc", list(encoders()))
+def test_host_build_matches_zlib(built, enc):
+    f = encoders()[enc]
+    for name, raw in payloads().items():
+        assert sens.inflate_host(f(raw), len(raw)) == raw, (enc, name)
+
+
+def test_longer_stream_is_truncated_to_the_frame(built):
+    raw = payloads()["depth"]
+    with pytest.raises(ScnError, match="longer than the frame"):          # generic hook reports it ...
+        sens.inflate_host(zlib.compress(raw), len(raw) - 100)
+
+
+@pytest.mark.parametrize("damage", ["header", "truncated", "bad_block", "bad_distance", "garbage"])
+def test_corrupt_streams_are_errors(built, damage):
+    raw = payloads()["depth"]; good = bytearray(zlib.compress(raw, 6))
+    if damage == "header": bad = bytes([0x79]) + bytes(good[1:])
+    elif damage == "truncated": bad = bytes(good[: len(good) // 2])
+    elif damage == "bad_block": bad = bytes(good[:2]) + bytes([0x07]) + bytes(good[3:])            # BTYPE = 3
+    elif damage == "bad_distance":                                                                   # fixed block: length 3, distance 1 with no output yet
+        bad = bytes([0x78, 0x01]) + bytes([0b00000011, 0b00000010, 0]) + bytes(8)
+    else: bad = bytes(good[:2]) + bytes(np.random.default_rng(1).integers(0, 256, 500).astype(np.uint8))
+    with pytest.raises(ScnError):
+        sens.inflate_host(bad, len(raw))

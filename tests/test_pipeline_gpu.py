@@ -97,3 +97,20 @@ def test_fuse_then_segment_end_to_end(built, tmp_path):
     # identical ids from the oracle on the same mesh
     assert (seg == ob.oracle_segment(xyz, tri)).all()
     assert 3 <= len(set(seg.tolist())) < len(xyz) // 20
+
+
+def test_fuse_gpu_decode_writes_the_same_mesh(built, tmp_path):
+    """`fuse` with the depth streams inflated on the GPU == `fuse` with the host decoder (same PLY bytes)."""
+    D, Cc, P, K = synth.make_frames(40, seed=5, width=160, height=120, loop_frames=600, invalid_pose_every=13, noise_mm=1.0, drop=0.02)
+    params = tmp_path / "params.txt"
+    params.write_text("s_SDFVoxelSize = 0.008f;\ns_SDFTruncation = 0.04f;\ns_SDFTruncationScale = 0.01f;\ns_hashNumSDFBlocks = 60000;\n")
+    out = {}
+    for mode in ("host", "gpu"):
+        d = tmp_path / mode; d.mkdir()
+        synth.write_sens(str(d / "scene.sens"), D, Cc, P, K, depth_comp=1, color_comp=0)
+        r = subprocess.run([os.path.join(BIN, "fuse"), str(params), str(d / "scene.sens")], capture_output=True, text=True,
+                           env=dict(os.environ, SCN_FUSE_DECODE=mode))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert ("GPU inflate" in r.stdout) == (mode == "gpu")
+        out[mode] = (d / "scene_vh.ply").read_bytes()
+    assert out["host"] == out["gpu"]
