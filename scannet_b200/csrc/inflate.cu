@@ -27,8 +27,18 @@ struct HuffTab {                     // canonical Huffman code, lengths 1..15
   uint16_t first[16];                // first code of each length
   uint16_t offs[16];                 // index of that code's symbol in sym[]
   uint16_t sym[288];
+  uint16_t fast[512];                // 9-bit lookahead (stream bit order) -> symbol | length << 9; 0 = code longer than 9 bits
 };
 struct InflateScratch { HuffTab lit, dist; uint8_t lens[320]; };
+
+// On the device the scratch lives in (dynamic) shared memory and is addressed directly; a generic pointer made the compiler
+// re-derive the shared window for every symbol.
+extern __shared__ __align__(16) unsigned char g_inflate_smem[];
+#ifdef __CUDA_ARCH__
+#define SCN_SCR(scr) (*reinterpret_cast<InflateScratch*>(g_inflate_smem))
+#else
+#define SCN_SCR(scr) (*(scr))
+#endif
 
 struct BitIn { const uint8_t* p; size_t n, pos; uint64_t bb; int bc; int over; };
 
@@ -56,24 +66,45 @@ SCN_HD unsigned rev_bits(unsigned v, int n) {
 #endif
 }
 
-// RFC 1951 3.2.5 base values / extra bits, packed as (base << 4 | extra)
+// RFC 1951 3.2.5 base values / extra bits, packed as (base << 4 | extra).  __constant__ on the device: a local array was
+// compiled into an 80-instruction select tree per lookup (46 % of all executed instructions in the first profile).
+#define SCN_LEN_TAB {3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 0, 6 << 4 | 0, 7 << 4 | 0, 8 << 4 | 0, 9 << 4 | 0, 10 << 4 | 0, 11 << 4 | 1, 13 << 4 | 1, \
+                     15 << 4 | 1, 17 << 4 | 1, 19 << 4 | 2, 23 << 4 | 2, 27 << 4 | 2, 31 << 4 | 2, 35 << 4 | 3, 43 << 4 | 3, 51 << 4 | 3, 59 << 4 | 3, \
+                     67 << 4 | 4, 83 << 4 | 4, 99 << 4 | 4, 115 << 4 | 4, 131 << 4 | 5, 163 << 4 | 5, 195 << 4 | 5, 227 << 4 | 5, 258 << 4 | 0}
+#define SCN_DIST_TAB {1 << 4 | 0, 2 << 4 | 0, 3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 1, 7 << 4 | 1, 9 << 4 | 2, 13 << 4 | 2, 17 << 4 | 3, 25 << 4 | 3, \
+                      33 << 4 | 4, 49 << 4 | 4, 65 << 4 | 5, 97 << 4 | 5, 129 << 4 | 6, 193 << 4 | 6, 257 << 4 | 7, 385 << 4 | 7, 513 << 4 | 8, 769 << 4 | 8, \
+                      1025 << 4 | 9, 1537 << 4 | 9, 2049 << 4 | 10, 3073 << 4 | 10, 4097 << 4 | 11, 6145 << 4 | 11, 8193 << 4 | 12, 12289 << 4 | 12, \
+                      16385 << 4 | 13, 24577 << 4 | 13}
+__constant__ unsigned c_len_tab[29] = SCN_LEN_TAB;
+__constant__ unsigned c_dist_tab[30] = SCN_DIST_TAB;
+static const unsigned h_len_tab[29] = SCN_LEN_TAB;
+static const unsigned h_dist_tab[30] = SCN_DIST_TAB;
 SCN_HD unsigned len_code(unsigned i) {
-  const unsigned t[29] = {3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 0, 6 << 4 | 0, 7 << 4 | 0, 8 << 4 | 0, 9 << 4 | 0, 10 << 4 | 0, 11 << 4 | 1, 13 << 4 | 1,
-                          15 << 4 | 1, 17 << 4 | 1, 19 << 4 | 2, 23 << 4 | 2, 27 << 4 | 2, 31 << 4 | 2, 35 << 4 | 3, 43 << 4 | 3, 51 << 4 | 3, 59 << 4 | 3,
-                          67 << 4 | 4, 83 << 4 | 4, 99 << 4 | 4, 115 << 4 | 4, 131 << 4 | 5, 163 << 4 | 5, 195 << 4 | 5, 227 << 4 | 5, 258 << 4 | 0};
-  return t[i];
+#ifdef __CUDA_ARCH__
+  return c_len_tab[i];
+#else
+  return h_len_tab[i];
+#endif
 }
 SCN_HD unsigned dist_code(unsigned i) {
-  const unsigned t[30] = {1 << 4 | 0, 2 << 4 | 0, 3 << 4 | 0, 4 << 4 | 0, 5 << 4 | 1, 7 << 4 | 1, 9 << 4 | 2, 13 << 4 | 2, 17 << 4 | 3, 25 << 4 | 3,
-                          33 << 4 | 4, 49 << 4 | 4, 65 << 4 | 5, 97 << 4 | 5, 129 << 4 | 6, 193 << 4 | 6, 257 << 4 | 7, 385 << 4 | 7, 513 << 4 | 8, 769 << 4 | 8,
-                          1025 << 4 | 9, 1537 << 4 | 9, 2049 << 4 | 10, 3073 << 4 | 10, 4097 << 4 | 11, 6145 << 4 | 11, 8193 << 4 | 12, 12289 << 4 | 12,
-                          16385 << 4 | 13, 24577 << 4 | 13};
-  return t[i];
+#ifdef __CUDA_ARCH__
+  return c_dist_tab[i];
+#else
+  return h_dist_tab[i];
+#endif
 }
 
-// canonical code from code lengths; returns false for an over-subscribed set (incomplete sets are allowed, as in zlib for
-// a single distance code)
-SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n) {
+template <int LANES>
+SCN_HD void lanes_sync() {
+#ifdef __CUDA_ARCH__
+  if (LANES > 1) __syncwarp();
+#endif
+}
+
+// canonical code from code lengths + the 9-bit lookahead table (filled by all lanes together); returns false for an
+// over-subscribed set (incomplete sets are allowed, as in zlib for a single distance code)
+template <int LANES>
+SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane) {
   for (int i = 0; i < 16; ++i) h.count[i] = 0;
   for (int i = 0; i < n; ++i) h.count[lens[i]]++;
   h.count[0] = 0;
@@ -84,15 +115,28 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n) {
     code = (code + h.count[l - 1]) << 1;
     h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += h.count[l];
   }
-  uint16_t next[16];
-  for (int l = 1; l < 16; ++l) next[l] = h.offs[l];
-  for (int i = 0; i < n; ++i) if (lens[i]) h.sym[next[lens[i]]++] = (uint16_t)i;
+  for (int j = lane; j < 512; j += LANES) h.fast[j] = 0;
+  lanes_sync<LANES>();
+  uint16_t nexti[16], nextc[16];
+  for (int l = 1; l < 16; ++l) { nexti[l] = h.offs[l]; nextc[l] = h.first[l]; }
+  for (int i = 0; i < n; ++i) {
+    const int l = lens[i];
+    if (!l) continue;
+    const unsigned c = nextc[l]++;
+    h.sym[nexti[l]++] = (uint16_t)i;
+    if (l <= 9) {
+      const unsigned r = rev_bits(c, l);
+      for (unsigned j = r + ((unsigned)lane << l); j < 512u; j += (unsigned)LANES << l) h.fast[j] = (uint16_t)(i | (l << 9));
+    }
+  }
   return true;
 }
 // decode one symbol (caller guarantees >= 15 bits in the buffer: bi_refill leaves > 32); -1 = invalid code
 SCN_HD int huff_decode(BitIn& b, const HuffTab& h) {
+  const unsigned e = h.fast[bi_peek(b, 9)];
+  if (e) { bi_drop(b, (int)(e >> 9)); return (int)(e & 511u); }
   const unsigned r = rev_bits(bi_peek(b, 15), 15);
-  for (int l = 1; l < 16; ++l) {
+  for (int l = 10; l < 16; ++l) {
     const unsigned c = (r >> (15 - l)) - h.first[l];
     if (c < h.count[l]) { bi_drop(b, l); return h.sym[h.offs[l] + c]; }
   }
@@ -110,13 +154,6 @@ SCN_HD int fixed_lit_decode(BitIn& b) {
 
 enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_BAD_DIST = 4, INF_OUT_FULL = 5, INF_TRUNCATED = 6 };
 
-template <int LANES>
-SCN_HD void lanes_sync() {
-#ifdef __CUDA_ARCH__
-  if (LANES > 1) __syncwarp();
-#endif
-}
-
 // Inflates one zlib stream.  Every lane executes this with identical arguments except `lane`; the output is written
 // cooperatively.  Returns INF_* and the number of bytes produced.
 template <int LANES>
@@ -126,6 +163,7 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
   const unsigned cmf = in[0], flg = in[1];
   if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return INF_BAD_HEADER;     // RFC 1950; preset dictionaries are not used
   BitIn b{in, n, 2, 0ull, 0, 0};
+  InflateScratch& S = SCN_SCR(scr);
   size_t o = 0;
   for (;;) {
     bi_refill(b);
@@ -153,13 +191,13 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
         for (int i = 0; i < 19; ++i) cl[i] = 0;
         for (int i = 0; i < hclen; ++i) { bi_refill(b); cl[order[i]] = (uint8_t)bi_get(b, 3); }
         lanes_sync<LANES>();                                      // previous block's tables are dead for every lane
-        if (!huff_build(scr->lit, cl, 19)) return INF_BAD_BLOCK;  // code-length code lives in the lit table for a moment
+        if (!huff_build<LANES>(S.lit, cl, 19, lane)) return INF_BAD_BLOCK;  // code-length code lives in the lit table for a moment
         lanes_sync<LANES>();
         int idx = 0;
-        uint8_t* lens = scr->lens;
+        uint8_t* lens = S.lens;
         while (idx < hlit + hdist) {
           bi_refill(b);
-          const int s = huff_decode(b, scr->lit);
+          const int s = huff_decode(b, S.lit);
           if (s < 0) return INF_BAD_CODE;
           if (s < 16) { lens[idx++] = (uint8_t)s; continue; }
           int rep; uint8_t v = 0;
@@ -171,12 +209,12 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
         }
         if (lens[256] == 0) return INF_BAD_BLOCK;
         lanes_sync<LANES>();
-        if (!huff_build(scr->lit, lens, hlit) || !huff_build(scr->dist, lens + hlit, hdist)) return INF_BAD_BLOCK;
+        if (!huff_build<LANES>(S.lit, lens, hlit, lane) || !huff_build<LANES>(S.dist, lens + hlit, hdist, lane)) return INF_BAD_BLOCK;
         lanes_sync<LANES>();
       }
       for (;;) {
         bi_refill(b);
-        const int s = type == 1 ? fixed_lit_decode(b) : huff_decode(b, scr->lit);
+        const int s = type == 1 ? fixed_lit_decode(b) : huff_decode(b, S.lit);
         if (s < 0) return INF_BAD_CODE;
         if (s < 256) {
           if (o >= cap) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
@@ -190,7 +228,7 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
         unsigned len = (lc >> 4) + bi_get(b, (int)(lc & 15u));
         bi_refill(b);
         int ds;
-        if (type == 1) ds = (int)rev_bits(bi_get(b, 5), 5); else ds = huff_decode(b, scr->dist);
+        if (type == 1) ds = (int)rev_bits(bi_get(b, 5), 5); else ds = huff_decode(b, S.dist);
         if (ds < 0 || ds > 29) return INF_BAD_CODE;
         const unsigned dc = dist_code((unsigned)ds);
         const unsigned dist = (dc >> 4) + bi_get(b, (int)(dc & 15u));
@@ -220,11 +258,10 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
 __global__ void __launch_bounds__(32) k_inflate(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ in_off, uint8_t* out,
                                                   size_t out_stride, size_t out_cap, unsigned n, int* __restrict__ status,
                                                   unsigned long long* __restrict__ produced) {
-  __shared__ InflateScratch scr;
   const unsigned s = blockIdx.x;
   if (s >= n) return;
   size_t got = 0;
-  const int rc = inflate_zlib<32>(in + in_off[s], (size_t)(in_off[s + 1] - in_off[s]), out + (size_t)s * out_stride, out_cap, (int)threadIdx.x, &scr, &got);
+  const int rc = inflate_zlib<32>(in + in_off[s], (size_t)(in_off[s + 1] - in_off[s]), out + (size_t)s * out_stride, out_cap, (int)threadIdx.x, nullptr, &got);
   if (threadIdx.x == 0) { status[s] = rc; produced[s] = got; }
 }
 
@@ -321,7 +358,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   }
   std::vector<int> status(n); std::vector<unsigned long long> prod(n);
   if (e == cudaSuccess) {
-    k_inflate<<<n, 32, 0, st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    k_inflate<<<n, 32, sizeof(InflateScratch), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
     e = cudaMemcpyAsync(status.data(), g.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(prod.data(), g.d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
