@@ -20,5 +20,7 @@ if [ "${NCU:-1}" = "1" ]; then
       python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu --no-seg > $OUT/ncu_full_$TAG.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_alloc -s 4 -c 1 -f -o $OUT/prof_alloc_$TAG \
       python bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu --no-seg > $OUT/ncu_full_alloc_$TAG.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_inflate -s 1 -c 1 -f -o $OUT/prof_inflate_$TAG \
+      python scripts/probes/inflate_probe.py 64 1 > $OUT/ncu_full_inflate_$TAG.log 2>&1
   tail -3 $OUT/ncu_full_$TAG.log
 fi
