@@ -444,9 +444,7 @@ def main():
                                  "block per launch) lower than the algorithmic figure, so frac may exceed 1"},
             "clocks": clocks,
         }
-        if not args.no_cpu and world == 1:          # CPU baseline: rank 0 at N=1 only
-            line["cpu_baseline"] = cpu_arm(args)
-        if world == 1 and not args.no_seg:
+        if world == 1 and not args.no_seg:          # side sections first: the 128-thread CPU arm below perturbs host-side timings measured after it
             try:
                 line["segmentator"] = seg_bench(args.seg_c5)
             except Exception as e:          # the side benchmarks must never take the headline line down
@@ -455,6 +453,8 @@ def main():
                 line["sens"] = sens_bench()
             except Exception as e:
                 line["sens"] = {"error": repr(e)}
+        if not args.no_cpu and world == 1:          # CPU baseline: rank 0 at N=1 only
+            line["cpu_baseline"] = cpu_arm(args)
         emit(line)
     grp.close()
 

@@ -40,7 +40,7 @@ extern __shared__ __align__(16) unsigned char g_inflate_smem[];
 #define SCN_SCR(scr) (*(scr))
 #endif
 
-struct BitIn { const uint8_t* p; size_t n, pos; uint64_t bb; int bc; int over; };
+struct BitIn { const uint8_t* p; uint32_t n, pos; uint64_t bb; int bc; int over; };   // streams and frames are far below 4 GB: 32-bit offsets halve the address arithmetic
 
 // Guarantees more than 32 valid bits (every decode step needs at most 32: a length code + extra bits is 20, a distance
 // code + extra bits 28, a stored-block header 32).  One aligned 32-bit load per four input bytes: the dependent chain of
@@ -157,14 +157,15 @@ enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_
 // Inflates one zlib stream.  Every lane executes this with identical arguments except `lane`; the output is written
 // cooperatively.  Returns INF_* and the number of bytes produced.
 template <int LANES>
-SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, int lane, InflateScratch* scr, size_t* produced) {
+SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap_in, int lane, InflateScratch* scr, size_t* produced) {
   *produced = 0;
-  if (n < 2) return INF_BAD_HEADER;
+  if (n_in < 2 || n_in > 0xFFFFFFF0ull || cap_in > 0xFFFFFFF0ull) return INF_BAD_HEADER;
+  const uint32_t n = (uint32_t)n_in, cap = (uint32_t)cap_in;
   const unsigned cmf = in[0], flg = in[1];
   if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return INF_BAD_HEADER;     // RFC 1950; preset dictionaries are not used
   BitIn b{in, n, 2, 0ull, 0, 0};
   InflateScratch& S = SCN_SCR(scr);
-  size_t o = 0;
+  uint32_t o = 0;
   for (;;) {
     bi_refill(b);
     const unsigned last = bi_get(b, 1), type = bi_get(b, 2);
@@ -174,10 +175,10 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n, uint8_t* out, size_t cap, i
       const unsigned len = bi_get(b, 16), nlen = bi_get(b, 16);
       if ((len ^ 0xFFFFu) != nlen || bi_overrun(b)) return INF_BAD_BLOCK;
       // the bytes still in the bit buffer come first, then straight from the input
-      const size_t src0 = b.pos - (size_t)((b.bc - b.over) / 8);
+      const uint32_t src0 = b.pos - (uint32_t)((b.bc - b.over) / 8);
       if (src0 + len > n) return INF_TRUNCATED;
-      const size_t take = o + len > cap ? cap - o : (size_t)len;
-      for (size_t i = (size_t)lane; i < take; i += LANES) out[o + i] = in[src0 + i];
+      const uint32_t take = o + len > cap ? cap - o : len;
+      for (uint32_t i = (uint32_t)lane; i < take; i += LANES) out[o + i] = in[src0 + i];
       o += take;
       if (take < len) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
       b.pos = src0 + len; b.bb = 0; b.bc = 0; b.over = 0;

@@ -26,8 +26,11 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <new>
 #include <thread>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include "scan.cuh"
 #include "scn_common.h"
@@ -591,7 +594,27 @@ inline void uf_prefetch(const UfElt* U, const Edge12* e, size_t i, size_t nE) {
     y = e[i + 8].b; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y);
   }
 }
-void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<UfElt>& u) {
+// The forest is random-accessed 12 M times per 2 M-vertex mesh: back it with transparent huge pages (a heap allocation of a
+// long-lived process is usually 4 KB-paged, which cost ~40 % in TLB misses) and keep it between calls.
+template <typename T> struct HugeAlloc {
+  using value_type = T;
+  HugeAlloc() = default;
+  template <typename U> HugeAlloc(const HugeAlloc<U>&) {}
+  T* allocate(size_t n) {
+    const size_t bytes = ((n * sizeof(T)) + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+    void* p = aligned_alloc(size_t(2) << 20, bytes ? bytes : (size_t(2) << 20));
+    if (!p) throw std::bad_alloc();
+    madvise(p, bytes, MADV_HUGEPAGE);
+    return (T*)p;
+  }
+  void deallocate(T* p, size_t) { free(p); }
+  template <typename U> bool operator==(const HugeAlloc<U>&) const { return true; }
+  template <typename U> bool operator!=(const HugeAlloc<U>&) const { return false; }
+};
+using Forest = std::vector<UfElt, HugeAlloc<UfElt>>;
+thread_local Forest g_forest;
+
+void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, Forest& u) {
   u.resize(nV);
   for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; u[i].thr = c; }
   UfElt* U = u.data();
@@ -605,7 +628,7 @@ void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, std::vector<Uf
     }
   }
 }
-void host_small_merge(const Edge12* e, size_t nE, int min_verts, std::vector<UfElt>& u) {
+void host_small_merge(const Edge12* e, size_t nE, int min_verts, Forest& u) {
   UfElt* U = u.data();
   for (size_t j = 0; j < nE; ++j) {
     uf_prefetch(U, e, j, nE);
@@ -667,7 +690,7 @@ __global__ void k_compact12(const Edge12* __restrict__ e, size_t nK, const unsig
   const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j < nK && keep[j]) out[pos[j]] = e[j];
 }
-int filter_small_merge(const Edge12* dE, size_t nK, const std::vector<UfElt>& u, int min_verts, cudaStream_t st, const Edge12** out, size_t* n_out) {
+int filter_small_merge(const Edge12* dE, size_t nK, const Forest& u, int min_verts, cudaStream_t st, const Edge12** out, size_t* n_out) {
   const size_t nV = u.size();
   int2* hps = (int2*)g_pinned_in.get(nV * 8);
   if (!hps) return scn::fail(SCN_ERR_CUDA, "cudaHostAlloc (forest upload)");
@@ -781,7 +804,7 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   rc = prune_and_download(dRec.as<Rec>(), dTri.as<unsigned>(), nullptr, nE, st, &hE, &nK, &dE);
   if (rc) return rc;
   g_timings[6] = lapt.lap();
-  std::vector<UfElt> u;
+  Forest& u = g_forest;
   host_kruskal(hE, nK, nV, kthr, u);
   g_timings[4] = lapt.lap();
   if (roots_after_kruskal) for (size_t q = 0; q < nV; ++q) { int y = (int)q; while (y != u[y].p) y = u[y].p; roots_after_kruskal[q] = y; }
@@ -838,7 +861,7 @@ int scn_segment_graph(int32_t n_verts, int64_t n_edges, void* edges, float c, in
   const Edge12* hK = nullptr; size_t nK = 0;
   rc = prune_and_download(dRec.as<Rec>(), nullptr, dSrc.as<Edge12>(), nE, st, &hK, &nK);
   if (rc) return rc;
-  std::vector<UfElt> u;
+  Forest& u = g_forest;
   host_kruskal(hK, nK, (size_t)n_verts, c, u);
   for (int v = 0; v < n_verts; ++v) {
     int y = v; while (y != u[y].p) y = u[y].p;
