@@ -587,13 +587,6 @@ inline int uf_find_full(UfElt* U, int x) {
   while (U[x].p != y) { const int n = U[x].p; U[x].p = y; x = n; }
   return y;
 }
-inline void uf_prefetch(const UfElt* U, const Edge12* e, size_t i, size_t nE) {
-  if (i + 48 < nE) { __builtin_prefetch(U + e[i + 48].a); __builtin_prefetch(U + e[i + 48].b); }
-  if (i + 8 < nE) {
-    int y = e[i + 8].a; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y);
-    y = e[i + 8].b; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y);
-  }
-}
 // The forest is random-accessed 12 M times per 2 M-vertex mesh: back it with transparent huge pages (a heap allocation of a
 // long-lived process is usually 4 KB-paged, which cost ~40 % in TLB misses) and keep it between calls.
 template <typename T> struct HugeAlloc {
@@ -618,20 +611,19 @@ void host_kruskal(const Edge12* e, size_t nE, size_t nV, float c, Forest& u) {
   u.resize(nV);
   for (size_t i = 0; i < nV; ++i) { u[i].rank = 0; u[i].size = 1; u[i].p = (int)i; u[i].thr = c; }
   UfElt* U = u.data();
+  // (the prefetch walk is written out here on purpose: factored into a helper taking `const UfElt*` the same statements
+  //  compiled into a loop that ran 120 ms instead of 84 ms on the 2 M-vertex mesh)
   for (size_t i = 0; i < nE; ++i) {
-    uf_prefetch(U, e, i, nE);
+    if (i + 48 < nE) { __builtin_prefetch(U + e[i + 48].a); __builtin_prefetch(U + e[i + 48].b); }
+    if (i + 8 < nE) { int y = e[i + 8].a; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y); y = e[i + 8].b; y = U[y].p; y = U[y].p; __builtin_prefetch(U + y); }
     int a = uf_find_full(U, e[i].a), b = uf_find_full(U, e[i].b);
-    if (a != b && e[i].w <= U[a].thr && e[i].w <= U[b].thr) {
-      uf_join(U, a, b);
-      a = uf_find_full(U, a);
-      U[a].thr = e[i].w + (c / (float)U[a].size);
-    }
+    if (a != b && e[i].w <= U[a].thr && e[i].w <= U[b].thr) { uf_join(U, a, b); a = uf_find_full(U, a); U[a].thr = e[i].w + (c / (float)U[a].size); }
   }
 }
 void host_small_merge(const Edge12* e, size_t nE, int min_verts, Forest& u) {
   UfElt* U = u.data();
   for (size_t j = 0; j < nE; ++j) {
-    uf_prefetch(U, e, j, nE);
+    if (j + 48 < nE) { __builtin_prefetch(U + e[j + 48].a); __builtin_prefetch(U + e[j + 48].b); }
     const int a = uf_find_full(U, e[j].a), b = uf_find_full(U, e[j].b);
     if (a != b && (U[a].size < min_verts || U[b].size < min_verts)) uf_join(U, a, b);
   }
