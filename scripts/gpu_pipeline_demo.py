@@ -32,13 +32,23 @@ def main():
         prm = os.path.join(d, "zParameters.txt")
         with open(prm, "w") as fh:
             fh.write("s_SDFVoxelSize = 0.004f;\ns_SDFTruncation = 0.02f;\ns_SDFTruncationScale = 0.01f;\ns_hashNumSDFBlocks = 3000000;\n")
+        # depth inflated on the GPU from the compressed payloads (whole scan resident in HBM), colour on the host pool
+        t0 = time.perf_counter()
+        rg = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "fuse"), prm, p, os.path.join(d, "gpu_decode.ply")], capture_output=True, text=True,
+                            env=dict(os.environ, SCN_FUSE_DECODE="gpu"))
+        out["fuse_gpu_decode_wall_s"] = time.perf_counter() - t0
+        out["fuse_gpu_decode_stdout"] = rg.stdout.strip().splitlines()[-4:]
         t0 = time.perf_counter()
         r = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "fuse"), prm, p], capture_output=True, text=True)
         out["fuse_wall_s"] = time.perf_counter() - t0
         out["fuse_rc"] = r.returncode
-        out["fuse_stdout"] = r.stdout.strip().splitlines()[-3:]
+        out["fuse_stdout"] = r.stdout.strip().splitlines()[-4:]
         if r.returncode:
             out["fuse_stderr"] = r.stderr[-400:]
+        try:
+            out["gpu_decode_ply_identical"] = open(os.path.join(d, "gpu_decode.ply"), "rb").read() == open(os.path.join(d, "scene_vh.ply"), "rb").read()
+        except OSError:
+            out["gpu_decode_ply_identical"] = None
         ply = os.path.join(d, "scene_vh.ply")
         if os.path.exists(ply):
             out["ply_mb"] = os.path.getsize(ply) / 1e6
