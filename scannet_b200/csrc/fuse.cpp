@@ -7,6 +7,9 @@
 // of the GPU; frames are handed over in pinned memory.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +20,32 @@
 #include "scn_common.h"
 
 namespace {
+
+// Persistent worker pool: run(fn) executes fn() on every worker and on the caller, and returns when all are done
+// (spawning 64 threads per 128-frame chunk cost ~3 ms of a ~10 ms chunk).
+class Pool {
+ public:
+  explicit Pool(unsigned workers) { for (unsigned i = 0; i < workers; ++i) th_.emplace_back([this]() { loop(); }); }
+  ~Pool() { { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+  void run(const std::function<void()>& fn) {
+    { std::lock_guard<std::mutex> l(m_); fn_ = &fn; pending_ = (unsigned)th_.size(); ++gen_; }
+    cv_.notify_all();
+    fn();
+    std::unique_lock<std::mutex> l(m_); done_.wait(l, [this]() { return pending_ == 0; });
+  }
+ private:
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void()>* fn;
+      { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&]() { return gen_ != seen; }); seen = gen_; if (stop_) return; fn = fn_; }
+      (*fn)();
+      { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+    }
+  }
+  std::vector<std::thread> th_; std::mutex m_; std::condition_variable cv_, done_;
+  const std::function<void()>* fn_ = nullptr; unsigned pending_ = 0; unsigned long gen_ = 0; bool stop_ = false;
+};
 
 struct Chunk { uint16_t* depth = nullptr; uint8_t* rgb = nullptr; std::vector<float> poses; uint32_t n = 0; int rc = 0; std::string err; };
 
@@ -33,12 +62,13 @@ void build_color_lut(const scn_sens_info_t& in, std::vector<int32_t>& lut) {
   }
 }
 
-void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vector<int32_t>& lut, bool use_color, bool want_depth, uint64_t f0, uint32_t n, Chunk& c, unsigned threads) {
+void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vector<int32_t>& lut, bool use_color, bool want_depth, uint64_t f0, uint32_t n, Chunk& c, Pool& pool) {
   const size_t px = (size_t)in.depth_width * in.depth_height;
   c.n = n; c.rc = 0; c.poses.assign((size_t)n * 16, 0.f);
   std::atomic<uint32_t> next{0}; std::atomic<int> rc{0};
   auto work = [&]() {
-    std::vector<uint8_t> col(use_color ? (size_t)in.color_width * in.color_height * 3 : 0);
+    static thread_local std::vector<uint8_t> col;                               // kept per pool thread: no 1-4 MB allocation per chunk
+    col.resize(use_color ? (size_t)in.color_width * in.color_height * 3 : 0);
     for (;;) {
       const uint32_t i = next.fetch_add(1);
       if (i >= n || rc.load()) break;
@@ -53,10 +83,7 @@ void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vecto
       if (r) { rc.store(r); }
     }
   };
-  std::vector<std::thread> pool;
-  for (unsigned t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
-  for (auto& t : pool) t.join();
+  pool.run(work);
   c.rc = rc.load();
   if (c.rc) c.err = scn_last_error();
 }
@@ -94,6 +121,7 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   // ~30 us): use up to 64 cores, and chunks of two frames per worker so that thread start-up is amortised
   const unsigned threads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
   const uint32_t CH = std::max(32u, 2 * threads);
+  Pool pool(threads - 1);
   Chunk ch[2];
   for (Chunk& c : ch) { c.depth = (uint16_t*)scn_host_alloc(CH * px * 2); c.rgb = use_color ? (uint8_t*)scn_host_alloc(CH * px * 3) : nullptr;
     if (!c.depth || (use_color && !c.rgb)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; } }
@@ -119,31 +147,47 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
     std::vector<float> poses;
     while (f < in.n_frames && !rc) {
       const uint32_t n = (uint32_t)std::min<uint64_t>(SUPER, in.n_frames - f);
-      int dec_rc = 0; std::string dec_err;
-      std::thread dec([&]() { dec_rc = scn_sens_decode_depth_device(s, f, n, d_depth, dec_stream); if (dec_rc) dec_err = scn_last_error(); });
+      int dec_rc = 0; std::string dec_err; std::atomic<bool> depth_done{false};
+      const auto ts0 = std::chrono::steady_clock::now();
+      double t_depth = 0, t_color = 0;
+      auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count(); };
+      std::thread dec([&]() { dec_rc = scn_sens_decode_depth_device(s, f, n, d_depth, dec_stream); if (dec_rc) dec_err = scn_last_error(); t_depth = since(); depth_done.store(true); });
       poses.assign((size_t)n * 16, 0.f);
+      uint32_t fused = 0;                                                      // frames of this super-chunk already handed to the integrator
+      auto fuse_upto = [&](uint32_t upto) {
+        if (upto <= fused) return 0;
+        const int r = scn_tsdf_integrate_device(vol, upto - fused, d_depth + (size_t)fused * px, use_color ? d_rgb + (size_t)fused * px * 3 : nullptr,
+                                                &poses[(size_t)fused * 16], in.depth_intrinsic);
+        fused = upto; return r;
+      };
       for (uint32_t c0 = 0; c0 < n && !rc; c0 += CH) {                       // colour (and poses) of this super-chunk, CH frames at a time
         const uint32_t cn = std::min<uint32_t>(CH, n - c0);
-        decode_chunk(s, in, lut, use_color, false, f + c0, cn, ch[0], threads);
+        decode_chunk(s, in, lut, use_color, false, f + c0, cn, ch[0], pool);
         if (ch[0].rc) { fprintf(stderr, "%s\n", ch[0].err.c_str()); rc = 1; break; }
         memcpy(&poses[(size_t)c0 * 16], ch[0].poses.data(), (size_t)cn * 64);
-        if (use_color && scn_memcpy_h2d(d_rgb + (size_t)c0 * px * 3, ch[0].rgb, (size_t)cn * px * 3, up_stream)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+        if (use_color && scn_memcpy_h2d(d_rgb + (size_t)c0 * px * 3, ch[0].rgb, (size_t)cn * px * 3, up_stream)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }
+        // once the depth of the whole super-chunk is in HBM, fusion follows the colour decode chunk by chunk
+        if (depth_done.load() && !dec_rc && fuse_upto(c0 + cn)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
       }
+      t_color = since();
+      const uint32_t fused_early = fused;
       dec.join();
       if (dec_rc) { fprintf(stderr, "%s\n", dec_err.c_str()); rc = 1; }
-      if (!rc && (scn_tsdf_integrate_device(vol, n, d_depth, d_rgb, poses.data(), in.depth_intrinsic) || scn_tsdf_sync(vol))) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+      if (!rc && (fuse_upto(n) || scn_tsdf_sync(vol))) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; }
+      if (getenv("SCN_TIMING")) fprintf(stderr, "[timing] super-chunk of %u frames: depth on GPU done at %.3f s, colour pool done at %.3f s (%u frames already fused), all fused at %.3f s\n",
+                                        n, t_depth, t_color, fused_early, since());
       f += n;
     }
     scn_device_free(d_depth); scn_device_free(d_rgb); scn_stream_destroy(dec_stream); scn_stream_destroy(up_stream);
   } else {
-    if (in.n_frames) decode_chunk(s, in, lut, use_color, true, 0, (uint32_t)std::min<uint64_t>(CH, in.n_frames), ch[0], threads);
+    if (in.n_frames) decode_chunk(s, in, lut, use_color, true, 0, (uint32_t)std::min<uint64_t>(CH, in.n_frames), ch[0], pool);
     while (f < in.n_frames && !rc) {
       Chunk& c = ch[cur];
       if (c.rc) { fprintf(stderr, "%s\n", c.err.c_str()); rc = 1; break; }
       // the GPU consumes chunk `cur` asynchronously while the host decodes the next one into the other buffer
       if (scn_tsdf_integrate_batch(vol, c.n, c.depth, c.rgb, c.poses.data(), in.depth_intrinsic)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }
       f += c.n;
-      if (f < in.n_frames) decode_chunk(s, in, lut, use_color, true, f, (uint32_t)std::min<uint64_t>(CH, in.n_frames - f), ch[cur ^ 1], threads);
+      if (f < in.n_frames) decode_chunk(s, in, lut, use_color, true, f, (uint32_t)std::min<uint64_t>(CH, in.n_frames - f), ch[cur ^ 1], pool);
       if (scn_tsdf_sync(vol)) { fprintf(stderr, "%s\n", scn_last_error()); rc = 1; break; }      // chunk `cur` may be overwritten next round
       cur ^= 1;
     }

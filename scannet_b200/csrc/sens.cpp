@@ -328,7 +328,7 @@ int scn_sens_frame_depth_u16(const scn_sens* s, uint64_t i, uint16_t* out) {
     return SCN_OK;
   }
   if (s->depth_comp == 1) {                                                                  // TYPE_ZLIB_USHORT :703-709
-    std::vector<uint8_t> raw;
+    static thread_local std::vector<uint8_t> raw;                                            // reused: decode pools call this from many threads
     if (scn::zlib_inflate(f.depth.data(), f.depth.size(), raw, want)) return scn::fail(SCN_ERR_FORMAT, "frame %llu: corrupt zlib depth stream", (unsigned long long)i);
     if (raw.size() < want) return scn::fail(SCN_ERR_FORMAT, "frame %llu: depth stream holds %zu bytes, need %zu", (unsigned long long)i, raw.size(), want);
     memcpy(out, raw.data(), want);
