@@ -56,3 +56,21 @@ def test_corrupt_streams_are_errors(built, damage):
     else: bad = bytes(good[:2]) + bytes(np.random.default_rng(1).integers(0, 256, 500).astype(np.uint8))
     with pytest.raises(ScnError):
         sens.inflate_host(bad, len(raw))
+
+
+def test_fuzz_against_zlib(built):
+    """random payload structure x random encoder settings: the host build of the GPU decoder must reproduce zlib's input"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), size=st.integers(0, 40000), alphabet=st.sampled_from([1, 2, 4, 16, 64, 256]),
+           repeat=st.integers(0, 3), level=st.integers(0, 9), strategy=st.sampled_from([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]),
+           wbits=st.integers(9, 15), memlevel=st.integers(1, 9))
+    def run(seed, size, alphabet, repeat, level, strategy, wbits, memlevel):
+        rng = np.random.default_rng(seed)
+        raw = rng.integers(0, alphabet, size).astype(np.uint8).tobytes()
+        for _ in range(repeat):                                       # long-distance repeats -> matches at many distances
+            cut = int(rng.integers(0, len(raw) + 1)); raw = raw + raw[:cut]
+        co = zlib.compressobj(level, zlib.DEFLATED, wbits, memlevel, strategy)
+        assert sens.inflate_host(co.compress(raw) + co.flush(), len(raw)) == raw
+    run()
