@@ -123,20 +123,24 @@ SCN_HD uint32_t make_entry(int mode, unsigned sym, unsigned len) {
 // over-subscribed set (incomplete sets are allowed, as in zlib for a single distance code)
 template <int LANES>
 SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mode) {
-  for (int i = 0; i < 16; ++i) h.count[i] = 0;
-  for (int i = 0; i < n; ++i) h.count[lens[i]]++;
-  h.count[0] = 0;
+  // counted privately by every lane (a read-modify-write on the shared table would race between lanes); the shared copies
+  // below are then written with identical values by all of them
+  uint16_t cnt[16];
+  for (int i = 0; i < 16; ++i) cnt[i] = 0;
+  for (int i = 0; i < n; ++i) cnt[lens[i]]++;
+  cnt[0] = 0;
   int left = 1; unsigned code = 0, off = 0;
+  h.count[0] = 0;
   for (int l = 1; l < 16; ++l) {
-    left = (left << 1) - (int)h.count[l];
+    left = (left << 1) - (int)cnt[l];
     if (left < 0) return false;
-    code = (code + h.count[l - 1]) << 1;
-    h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += h.count[l];
+    code = (code + cnt[l - 1]) << 1;
+    h.count[l] = cnt[l]; h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += cnt[l];
   }
   for (int j = lane; j < 512; j += LANES) h.fast[j] = 0;
   lanes_sync<LANES>();
   uint16_t nexti[16], nextc[16];
-  for (int l = 1; l < 16; ++l) { nexti[l] = h.offs[l]; nextc[l] = h.first[l]; }
+  { unsigned c2 = 0, o2 = 0; for (int l = 1; l < 16; ++l) { c2 = (c2 + cnt[l - 1]) << 1; nextc[l] = (uint16_t)c2; nexti[l] = (uint16_t)o2; o2 += cnt[l]; } }
   for (int i = 0; i < n; ++i) {
     const int l = lens[i];
     if (!l) continue;
@@ -207,20 +211,24 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
         lanes_sync<LANES>();
         int idx = 0;
         uint8_t* lens = S.lens;
+        uint8_t prev = 0, eob_len = 0;
         while (idx < hlit + hdist) {
           bi_refill(b);
           const uint32_t ce = huff_decode(b, S.lit, M_PLAIN);
           if (((ce >> 8) & 3u) != K_LIT) return INF_BAD_CODE;
           const int s = (int)(ce >> 16);
-          if (s < 16) { lens[idx++] = (uint8_t)s; continue; }
+          // `prev` and `eob_len` live in registers: every lane writes the same bytes to the shared array, nobody reads it here
+          if (s < 16) { if (idx == 256) eob_len = (uint8_t)s; lens[idx++] = prev = (uint8_t)s; continue; }
           int rep; uint8_t v = 0;
-          if (s == 16) { if (idx == 0) return INF_BAD_BLOCK; v = lens[idx - 1]; rep = 3 + (int)bi_get(b, 2); }
+          if (s == 16) { if (idx == 0) return INF_BAD_BLOCK; v = prev; rep = 3 + (int)bi_get(b, 2); }
           else if (s == 17) rep = 3 + (int)bi_get(b, 3);
           else rep = 11 + (int)bi_get(b, 7);
           if (idx + rep > hlit + hdist) return INF_BAD_BLOCK;
+          if (idx <= 256 && 256 < idx + rep) eob_len = v;
+          prev = v;
           while (rep--) lens[idx++] = v;
         }
-        if (lens[256] == 0) return INF_BAD_BLOCK;
+        if (eob_len == 0) return INF_BAD_BLOCK;
         lanes_sync<LANES>();
         if (!huff_build<LANES>(S.lit, lens, hlit, lane, M_LITLEN) || !huff_build<LANES>(S.dist, lens + hlit, hdist, lane, M_DIST)) return INF_BAD_BLOCK;
         lanes_sync<LANES>();
