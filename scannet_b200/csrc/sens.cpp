@@ -28,6 +28,7 @@ int jpeg_decode_rgb8(const uint8_t* data, size_t n, uint32_t want_w, uint32_t wa
 int png_decode_rgb8(const uint8_t* data, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out);    // jpeg.cpp
 int zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t size_hint);
 void zlib_deflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out);
+void png_encode_stb(const uint8_t* px, uint32_t w, uint32_t h, int n, std::vector<uint8_t>& out);
 }  // namespace scn
 
 // ------------------------------------------------------------------------------ inflate (RFC 1950/1951)
@@ -188,41 +189,130 @@ void put_litlen(BitWriter& bw, int sym) {
 }
 }  // namespace
 
+// The reference compresses depth (and the PNGs of saveToImages) with stb_image_write v1.00's zlib writer
+// (sensorData.h:667, sensorData/stb_image_write.h:721-824): one fixed-Huffman block, greedy LZ77 with a one-byte lazy check,
+// 16384 hash buckets that keep the most recent `quality`..2*quality positions.  Every decision below is the same decision, so
+// a stream written here is byte-identical to the reference writer's (tests/test_sens_cpu.py):
+//   * a candidate is usable if it is less than 32768 back (32767 for the lazy check), the longest match wins and of equal
+//     matches the most recently inserted one (>=), matches shorter than 3 are literals;
+//   * only positions where a search started are inserted; a bucket that reached 2*quality drops its older half first;
+//   * the last 3 bytes are literals.
 void scn::zlib_deflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+  const int quality = 8;                                        // compressDepth / stbi_write_png_to_mem both pass 8
   out.clear();
   out.push_back(0x78); out.push_back(0x5E);
   BitWriter bw(out);
   bw.put(1, 1); bw.put(1, 2);                                   // final block, fixed Huffman
-  const int HB = 15; std::vector<int32_t> head(1 << HB, -1), prev(n ? n : 1, -1);
-  auto hash = [&](size_t i) { return (uint32_t)((src[i] << 10) ^ (src[i + 1] << 5) ^ src[i + 2]) & ((1u << HB) - 1); };
-  size_t i = 0;
-  while (i < n) {
-    int best_len = 0; size_t best_dist = 0;
-    if (i + 3 <= n) {
-      const uint32_t h = hash(i);
-      int32_t c = head[h]; int chain = 16;
-      while (c >= 0 && chain-- && i - (size_t)c <= 32768) {
-        int l = 0; const int maxl = (int)std::min<size_t>(258, n - i);
-        while (l < maxl && src[c + l] == src[i + l]) ++l;
-        if (l > best_len) { best_len = l; best_dist = i - (size_t)c; if (l == maxl) break; }
-        c = prev[c];
+  constexpr uint32_t kBuckets = 16384;
+  struct Bucket { int32_t pos[16]; int n = 0; };                // 2*quality slots
+  std::vector<Bucket> table(kBuckets);
+  auto hash3 = [&](size_t i) {
+    uint32_t h = (uint32_t)src[i] + ((uint32_t)src[i + 1] << 8) + ((uint32_t)src[i + 2] << 16);
+    h ^= h << 3; h += h >> 5; h ^= h << 4; h += h >> 17; h ^= h << 25; h += h >> 6;
+    return h & (kBuckets - 1);
+  };
+  auto match_len = [&](size_t a, size_t b, size_t limit) {      // common prefix of src[a..] and src[b..], at most min(limit, 258)
+    size_t l = 0; const size_t m = limit < 258 ? limit : 258;
+    while (l < m && src[a + l] == src[b + l]) ++l;
+    return (int)l;
+  };
+  const long N = (long)n;
+  long i = 0;
+  while (i < N - 3) {
+    Bucket& bk = table[hash3((size_t)i)];
+    int best = 3; long best_pos = -1;
+    for (int j = 0; j < bk.n; ++j) {
+      if ((long)bk.pos[j] > i - 32768) {
+        const int d = match_len((size_t)bk.pos[j], (size_t)i, (size_t)(N - i));
+        if (d >= best) { best = d; best_pos = bk.pos[j]; }
       }
     }
-    const size_t step = best_len >= 3 ? (size_t)best_len : 1;
-    if (best_len >= 3) {
-      int li = 28; while (kLenBase[li] > best_len) --li;
-      put_litlen(bw, 257 + li); bw.put((uint32_t)(best_len - kLenBase[li]), kLenExtra[li]);
-      int di = 29; while (kDistBase[di] > best_dist) --di;
-      bw.put_rev((uint32_t)di, 5); bw.put((uint32_t)(best_dist - kDistBase[di]), kDistExtra[di]);
-    } else put_litlen(bw, src[i]);
-    for (size_t k = 0; k < step; ++k, ++i) if (i + 3 <= n) { const uint32_t h = hash(i); prev[i] = head[h]; head[h] = (int32_t)i; }
+    if (bk.n == 2 * quality) { memmove(bk.pos, bk.pos + quality, sizeof(int32_t) * quality); bk.n = quality; }
+    bk.pos[bk.n++] = (int32_t)i;
+    if (best_pos >= 0) {                                        // a longer match starting one byte later turns this byte into a literal
+      const Bucket& nb = table[hash3((size_t)i + 1)];
+      for (int j = 0; j < nb.n; ++j) {
+        if ((long)nb.pos[j] > i - 32767 && match_len((size_t)nb.pos[j], (size_t)i + 1, (size_t)(N - i - 1)) > best) { best_pos = -1; break; }
+      }
+    }
+    if (best_pos >= 0) {
+      const int dist = (int)(i - best_pos);
+      int li = 0; while (li < 28 && best >= kLenBase[li + 1]) ++li;
+      put_litlen(bw, 257 + li); if (kLenExtra[li]) bw.put((uint32_t)(best - kLenBase[li]), kLenExtra[li]);
+      int di = 0; while (di < 29 && dist >= kDistBase[di + 1]) ++di;
+      bw.put_rev((uint32_t)di, 5); if (kDistExtra[di]) bw.put((uint32_t)(dist - kDistBase[di]), kDistExtra[di]);
+      i += best;
+    } else { put_litlen(bw, src[i]); ++i; }
   }
+  for (; i < N; ++i) put_litlen(bw, src[i]);
   put_litlen(bw, 256);
   bw.flush();
   uint32_t a = 1, b = 0;
   for (size_t k = 0; k < n; ++k) { a = (a + src[k]) % 65521u; b = (b + a) % 65521u; }
   const uint32_t ad = (b << 16) | a;
   out.push_back((uint8_t)(ad >> 24)); out.push_back((uint8_t)(ad >> 16)); out.push_back((uint8_t)(ad >> 8)); out.push_back((uint8_t)ad);
+}
+
+// PNG as stb_image_write v1.00 writes it (stb_image_write.h:851-941), which is what saveToImages produces for TYPE_RAW colour
+// (sensorData.h:1432-1440 via compressColor): 8-bit, no interlace, per row the filter with the smallest sum of |signed byte|
+// (first of equals; row 0 tries none / sub / none / half-of-left / sub under the labels 0..4), one IDAT, the zlib writer above.
+void scn::png_encode_stb(const uint8_t* px, uint32_t w, uint32_t h, int n, std::vector<uint8_t>& out) {
+  const size_t row = (size_t)w * n;
+  std::vector<uint8_t> filt((row + 1) * h);
+  std::vector<int8_t> line(row ? row : 1);
+  auto paeth = [](int a, int b, int c) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                                         return pa <= pb && pa <= pc ? a : (pb <= pc ? b : c); };
+  for (uint32_t j = 0; j < h; ++j) {
+    static const int later[5] = {0, 1, 2, 3, 4}, first[5] = {0, 1, 0, 5, 6};
+    const int* map = j ? later : first;
+    const uint8_t* z = px + row * j;
+    auto apply = [&](int type) {
+      for (size_t i = 0; i < row; ++i) {
+        const int cur = z[i], left = i >= (size_t)n ? z[i - n] : 0;
+        const int up = (type == 2 || type == 3 || type == 4) ? z[(long)i - (long)row] : 0;
+        const int ul = (type == 4 && i >= (size_t)n) ? z[(long)i - (long)row - n] : 0;
+        int v;
+        switch (type) {
+          case 0: v = cur; break;
+          case 1: v = cur - left; break;
+          case 2: v = cur - up; break;
+          case 3: v = cur - ((left + up) >> 1); break;
+          case 4: v = cur - paeth(left, up, ul); break;
+          case 5: v = cur - (left >> 1); break;
+          default: v = cur - left; break;                       // 6: paeth(left, 0, 0) == left
+        }
+        line[i] = (int8_t)(uint8_t)v;
+      }
+    };
+    int best = 0; long bestval = 0x7fffffff;
+    for (int k = 0; k < 5; ++k) {
+      apply(map[k]);
+      long est = 0; for (size_t i = 0; i < row; ++i) est += std::abs((int)line[i]);
+      if (est < bestval) { bestval = est; best = k; }
+    }
+    apply(map[best]);
+    filt[j * (row + 1)] = (uint8_t)best;
+    memcpy(&filt[j * (row + 1) + 1], line.data(), row);
+  }
+  std::vector<uint8_t> z;
+  zlib_deflate(filt.data(), filt.size(), z);
+  static uint32_t crc_table[256]; static bool crc_ready = false;
+  if (!crc_ready) { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1) ? 0xedb88320u : 0u); crc_table[i] = c; } crc_ready = true; }
+  auto be32 = [&](uint32_t v) { out.push_back((uint8_t)(v >> 24)); out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)v); };
+  auto chunk = [&](const char* tag, const uint8_t* d, size_t len) {
+    be32((uint32_t)len);
+    const size_t c0 = out.size();
+    out.insert(out.end(), tag, tag + 4); out.insert(out.end(), d, d + len);
+    uint32_t crc = ~0u; for (size_t i = c0; i < out.size(); ++i) crc = (crc >> 8) ^ crc_table[out[i] ^ (crc & 0xff)];
+    be32(~crc);
+  };
+  out.clear();
+  static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+  out.insert(out.end(), sig, sig + 8);
+  static const int ctype[5] = {-1, 0, 4, 2, 6};
+  uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h,
+                      8, (uint8_t)ctype[n], 0, 0, 0};
+  chunk("IHDR", ihdr, 13); chunk("IDAT", z.data(), z.size()); chunk("IEND", nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------ container
@@ -490,12 +580,16 @@ int scn_sens_save_to_images(const scn_sens* s, const char* out_dir) {
       if (!fp) return scn::fail(SCN_ERR_IO, "cannot open file %s", cf.c_str());
       fwrite(f.color.data(), 1, f.color.size(), fp); fclose(fp);
     } else if (s->color_comp == 0) {
-      // the reference re-encodes raw colour as PNG through stb_image_write (:1417-1425); we write the
-      // same pixels as a binary PPM next to it instead (documented deviation)
-      const std::string cf = counter_name(base, (unsigned)i, "color.ppm", 6);
+      // TYPE_RAW colour is re-encoded as frame-XXXXXX.color.png (sensorData.h:1410-1440).  The reference does that through its
+      // uplink codec (Windows builds); built without it, as here, it throws "need UPLINK_COMPRESSION" (:592).  We write the
+      // PNG with the stb_image_write-compatible encoder above.
+      const std::string cf = counter_name(base, (unsigned)i, "color.png", 6);
+      if (f.color.size() < (size_t)s->cw * s->ch * 3) return scn::fail(SCN_ERR_FORMAT, "invalid data");
+      std::vector<uint8_t> png;
+      scn::png_encode_stb(f.color.data(), s->cw, s->ch, 3, png);
       FILE* fp = fopen(cf.c_str(), "wb");
       if (!fp) return scn::fail(SCN_ERR_IO, "cannot open file %s", cf.c_str());
-      fprintf(fp, "P6\n%u %u\n255\n", s->cw, s->ch); fwrite(f.color.data(), 1, f.color.size(), fp); fclose(fp);
+      fwrite(png.data(), 1, png.size(), fp); fclose(fp);
     } else return scn::fail(SCN_ERR_FORMAT, "unknown format");
     int rc = scn_sens_frame_depth_u16(s, i, depth.data());
     if (rc) return rc;
