@@ -10,8 +10,8 @@
 //   * YCbCr -> RGB in 20-bit fixed point with the masked Cb term (stb_image.h:3091-3118)
 //   * coefficients truncated to int16 after de-quantisation (:1735,1764)
 // Structure (marker parser, canonical Huffman decoder, plane layout) is this repo's own.
-// Supported: SOF0/SOF1 8-bit, 1 or 3 components, interleaved and non-interleaved scans, restart markers.
-// Progressive (SOF2) files are rejected with SCN_ERR_UNSUPPORTED.
+// Supported: SOF0/SOF1 and progressive SOF2 (spectral selection + successive approximation, stb_image.h:1771-1913, 2582-2600),
+// 8-bit, 1 or 3 components, interleaved and non-interleaved scans, restart markers.
 #include <algorithm>
 #include <cstdlib>
 #include <cstdint>
@@ -67,7 +67,7 @@ struct HuffTab {
   }
 };
 
-struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0, x = 0, y = 0, w2 = 0, h2 = 0; std::vector<uint8_t> data; };
+struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0, x = 0, y = 0, w2 = 0, h2 = 0, coeff_w = 0; std::vector<uint8_t> data; std::vector<short> coeff; };
 
 struct Bits {
   const uint8_t* p; size_t n, pos; uint32_t buf = 0; int cnt = 0; bool hit_marker = false;
@@ -203,6 +203,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
     PlaneLease(Comp* c_, std::vector<uint8_t>* t_, int n_) : c(c_), t(t_), n(n_) { for (int i = 0; i < n; ++i) c[i].data.swap(t[i]); }
     ~PlaneLease() { for (int i = 0; i < n; ++i) c[i].data.swap(t[i]); }
   } lease(comp, tl_planes, 3); int ncomp = 0, W = 0, H = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0, restart = 0;
+  bool progressive = false;
   bool have_frame = false;
   size_t pos = 2;
   for (;;) {
@@ -235,8 +236,8 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         s += 17 + tot; sl -= 17 + tot;
       }
     } else if (m == 0xDD) { if (sl < 2) return fail(SCN_ERR_FORMAT, "bad DRI"); restart = (s[0] << 8) | s[1]; }
-    else if (m == 0xC2) return fail(SCN_ERR_UNSUPPORTED, "progressive JPEG is not supported");
-    else if (m == 0xC0 || m == 0xC1) {
+    else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+      progressive = m == 0xC2;
       if (sl < 6 || s[0] != 8) return fail(SCN_ERR_UNSUPPORTED, "only 8-bit JPEG");
       H = (s[1] << 8) | s[2]; W = (s[3] << 8) | s[4]; ncomp = s[5];
       if ((ncomp != 1 && ncomp != 3) || sl < (size_t)(6 + 3 * ncomp) || W == 0 || H == 0) return fail(SCN_ERR_FORMAT, "bad SOF");
@@ -250,6 +251,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         comp[i].x = (W * comp[i].h + hmax - 1) / hmax; comp[i].y = (H * comp[i].v + vmax - 1) / vmax;
         comp[i].w2 = mcux * comp[i].h * 8; comp[i].h2 = mcuy * comp[i].v * 8;
         comp[i].data.assign((size_t)comp[i].w2 * comp[i].h2 + 15, 0);
+        if (progressive) { comp[i].coeff_w = comp[i].w2 >> 3; comp[i].coeff.assign((size_t)comp[i].coeff_w * (comp[i].h2 >> 3) * 64, 0); }
       }
       have_frame = true;
     } else if (m == 0xDA) {
@@ -262,9 +264,22 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         for (int c = 0; c < ncomp; ++c) if (comp[c].id == s[1 + 2 * i]) which = c;
         if (which < 0) return fail(SCN_ERR_FORMAT, "bad SOS component");
         comp[which].td = s[2 + 2 * i] >> 4; comp[which].ta = s[2 + 2 * i] & 15;
-        if (comp[which].td > 3 || comp[which].ta > 3 || !hdc[comp[which].td].present || !hac[comp[which].ta].present || !have_q[comp[which].tq])
-          return fail(SCN_ERR_FORMAT, "scan references a missing table");
+        if (comp[which].td > 3 || comp[which].ta > 3 || !have_q[comp[which].tq]) return fail(SCN_ERR_FORMAT, "scan references a missing table");
         order[i] = which;
+      }
+      // spectral selection / successive approximation (stb_image.h:2665-2702)
+      const int spec_start = s[1 + 2 * ns], spec_end_raw = s[2 + 2 * ns], succ_high = s[3 + 2 * ns] >> 4, succ_low = s[3 + 2 * ns] & 15;
+      int spec_end = spec_end_raw;
+      if (progressive) {
+        if (spec_start > 63 || spec_end > 63 || spec_start > spec_end || succ_high > 13 || succ_low > 13) return fail(SCN_ERR_FORMAT, "bad SOS");
+      } else {
+        if (spec_start != 0 || succ_high != 0 || succ_low != 0) return fail(SCN_ERR_FORMAT, "bad SOS");
+        spec_end = 63;
+      }
+      for (int i = 0; i < ns; ++i) {
+        const Comp& c = comp[order[i]];
+        const bool need_dc = !progressive || spec_start == 0, need_ac = !progressive || spec_start != 0;
+        if ((need_dc && !hdc[c.td].present) || (need_ac && !hac[c.ta].present)) return fail(SCN_ERR_FORMAT, "scan references a missing table");
       }
       Bits br{d, n, pos + len};
       for (int c = 0; c < ncomp; ++c) comp[c].dc_pred = 0;
@@ -298,8 +313,76 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         idct8x8(c.data.data() + (size_t)c.w2 * by * 8 + (size_t)bx * 8, c.w2, blk);
         return true;
       };
+      int eob_run = 0;
+      // progressive passes write into the persistent coefficient blocks (stb_image.h:1771-1913); same arithmetic, in shorts
+      auto prog_dc = [&](Comp& c, short* data) -> bool {
+        if (spec_end != 0) return false;                                     // "can't merge dc and ac"
+        if (succ_high == 0) {
+          memset(data, 0, 64 * sizeof(short));
+          const int t = br.decode(hdc[c.td]);
+          if (t < 0 || t > 16) return false;
+          const int diff = t ? extend(br.get(t), t) : 0;
+          c.dc_pred += diff;
+          data[0] = (short)(c.dc_pred << succ_low);
+        } else if (br.get(1)) data[0] += (short)(1 << succ_low);
+        return true;
+      };
+      auto prog_ac = [&](Comp& c, short* data) -> bool {
+        if (spec_start == 0) return false;
+        const HuffTab& ha = hac[c.ta];
+        if (succ_high == 0) {
+          const int shift = succ_low;
+          if (eob_run) { --eob_run; return true; }
+          int k = spec_start;
+          do {
+            if (br.cnt < 16) br.fill();
+            const int fa = ha.fast_ac[br.buf >> (32 - kFastBits)];
+            if (fa) {
+              k += (fa >> 4) & 15;
+              const int used = fa & 15;
+              br.buf <<= used; br.cnt -= used;
+              data[kZig[k++ & 63]] = (short)((fa >> 8) << shift);
+            } else {
+              const int rs = br.decode(ha);
+              if (rs < 0) return false;
+              const int sz = rs & 15, r = rs >> 4;
+              if (sz == 0) {
+                if (r < 15) { eob_run = 1 << r; if (r) eob_run += br.get(r); --eob_run; break; }
+                k += 16;
+              } else { k += r; data[kZig[k++ & 63]] = (short)(extend(br.get(sz), sz) << shift); }
+            }
+          } while (k <= spec_end);
+        } else {
+          const short bit = (short)(1 << succ_low);
+          auto refine = [&](short* p) { if (br.get(1) && (*p & bit) == 0) { if (*p > 0) *p += bit; else *p -= bit; } };
+          if (eob_run) {
+            --eob_run;
+            for (int k = spec_start; k <= spec_end; ++k) { short* p = &data[kZig[k]]; if (*p != 0) refine(p); }
+          } else {
+            int k = spec_start;
+            do {
+              const int rs = br.decode(ha);
+              if (rs < 0) return false;
+              int sz = rs & 15, r = rs >> 4;
+              if (sz == 0) {
+                if (r < 15) { eob_run = (1 << r) - 1; if (r) eob_run += br.get(r); r = 64; }
+              } else {
+                if (sz != 1) return false;
+                sz = br.get(1) ? bit : -bit;
+              }
+              while (k <= spec_end) {
+                short* p = &data[kZig[k++]];
+                if (*p != 0) refine(p);
+                else { if (r == 0) { *p = (short)sz; break; } --r; }
+              }
+            } while (k <= spec_end);
+          }
+        }
+        return true;
+      };
       auto handle_restart = [&]() {
         if (--todo <= 0) {
+          eob_run = 0;
           // byte-align, expect RSTn
           br.reset();
           size_t q = br.pos;
@@ -312,18 +395,23 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
         return true;
       };
       bool ended = false;
+      auto one_block = [&](Comp& c, int bx, int by) -> bool {
+        if (!progressive) return decode_block(c, bx, by);
+        short* data = c.coeff.data() + 64 * ((size_t)bx + (size_t)by * c.coeff_w);
+        return (ns > 1 || spec_start == 0) ? prog_dc(c, data) : prog_ac(c, data);        // interleaved progressive scans are DC scans
+      };
       if (ns == 1) {
         Comp& c = comp[order[0]];
         const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
         for (int j = 0; j < bh && !ended; ++j) for (int i = 0; i < bw; ++i) {
-          if (!decode_block(c, i, j)) return fail(SCN_ERR_FORMAT, "bad huffman code");
+          if (!one_block(c, i, j)) return fail(SCN_ERR_FORMAT, "bad huffman code");
           if (!handle_restart()) { ended = true; break; }
         }
       } else {
         for (int j = 0; j < mcuy && !ended; ++j) for (int i = 0; i < mcux; ++i) {
           for (int k = 0; k < ns; ++k) { Comp& c = comp[order[k]];
             for (int y = 0; y < c.v; ++y) for (int x = 0; x < c.h; ++x)
-              if (!decode_block(c, i * c.h + x, j * c.v + y)) return fail(SCN_ERR_FORMAT, "bad huffman code"); }
+              if (!one_block(c, i * c.h + x, j * c.v + y)) return fail(SCN_ERR_FORMAT, "bad huffman code"); }
           if (!handle_restart()) { ended = true; break; }
         }
       }
@@ -335,6 +423,18 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
     pos += len;
   }
   if (!have_frame) return fail(SCN_ERR_FORMAT, "no frame in JPEG");
+  if (progressive) {                                                          // stbi__jpeg_finish: dequantise (in shorts) + IDCT of every real block
+    for (int k = 0; k < ncomp; ++k) {
+      Comp& c = comp[k];
+      if (!have_q[c.tq]) return fail(SCN_ERR_FORMAT, "scan references a missing table");
+      const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+      for (int j = 0; j < bh; ++j) for (int i = 0; i < bw; ++i) {
+        short* data = c.coeff.data() + 64 * ((size_t)i + (size_t)j * c.coeff_w);
+        for (int q = 0; q < 64; ++q) data[q] = (short)(data[q] * quant[c.tq][q]);
+        idct8x8(c.data.data() + (size_t)c.w2 * j * 8 + (size_t)i * 8, c.w2, data);
+      }
+    }
+  }
   if ((uint32_t)W != want_w || (uint32_t)H != want_h) return fail(SCN_ERR_FORMAT, "JPEG is %dx%d, header says %ux%u", W, H, want_w, want_h);
   // up-sample + colour convert, row by row (stb_image.h:3166-3250)
   struct Res { int hs, vs, ystep, wl, ypos; const uint8_t *l0, *l1; std::vector<uint8_t> buf; } rs[3];
@@ -368,7 +468,8 @@ int zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t
 // PNG colour frames (TYPE_PNG, sensorData.h:346-351; decoded by stbi_load_from_memory with 3 requested channels,
 // :609-616).  PNG is lossless, so any conforming decoder returns the reference's bytes; conversions to RGB follow
 // stb_image v2.08 (grey replicated, alpha dropped, palette expanded; 16-bit PNGs are rejected there and here).
-// Non-interlaced images only (Adam7 is rejected).
+// Adam7-interlaced images are scattered pass by pass (stb_image.h:4310-4350).  At 1/2/4-bit depth stb v2.08 takes the
+// "previous row" of the up/avg/paeth filters from uninitialised memory (:4003-4012); this decoder follows the PNG specification.
 int png_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out) {
   static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
   if (n < 8 || memcmp(d, sig, 8)) return fail(SCN_ERR_FORMAT, "not a PNG");
@@ -390,39 +491,59 @@ int png_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_h
   }
   if (!have_hdr || idat.empty()) return fail(SCN_ERR_FORMAT, "PNG without IHDR/IDAT");
   if (W != want_w || H != want_h) return fail(SCN_ERR_FORMAT, "PNG is %ux%u, header says %ux%u", W, H, want_w, want_h);
-  if (interlace) return fail(SCN_ERR_UNSUPPORTED, "interlaced PNG is not supported");
+  if (interlace > 1) return fail(SCN_ERR_FORMAT, "bad PNG interlace method");
   if (depth == 16) return fail(SCN_ERR_UNSUPPORTED, "PNG not supported: 1/2/4/8-bit only");          // as stb_image v2.08
   if (!(depth == 8 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return fail(SCN_ERR_FORMAT, "bad PNG bit depth");
   const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
   if (!ch) return fail(SCN_ERR_FORMAT, "bad PNG colour type");
-  const size_t bpp = std::max<size_t>(1, (size_t)ch * depth / 8), stride = ((size_t)W * ch * depth + 7) / 8;
+  const size_t bpp = std::max<size_t>(1, (size_t)ch * depth / 8);
+  auto pass_bytes = [&](uint32_t pw, uint32_t ph) { return pw && ph ? ((((size_t)pw * ch * depth + 7) >> 3) + 1) * ph : (size_t)0; };
+  // Adam7 (stb_image.h:4310-4350): seven sub-images, each filtered like a small PNG, scattered on an 8x8 lattice
+  static const uint32_t xorig[7] = {0, 4, 0, 2, 0, 1, 0}, yorig[7] = {0, 0, 4, 0, 2, 0, 1}, xspc[7] = {8, 8, 4, 4, 2, 2, 1}, yspc[7] = {8, 8, 8, 4, 4, 2, 2};
+  size_t need = 0;
+  if (interlace) { for (int p = 0; p < 7; ++p) need += pass_bytes((W - xorig[p] + xspc[p] - 1) / xspc[p], (H - yorig[p] + yspc[p] - 1) / yspc[p]); }
+  else need = pass_bytes(W, H);
   std::vector<uint8_t> raw;
-  if (zlib_inflate(idat.data(), idat.size(), raw, (stride + 1) * H) || raw.size() < (stride + 1) * H) return fail(SCN_ERR_FORMAT, "corrupt PNG data");
-  std::vector<uint8_t> prev(stride, 0), cur(stride);
-  for (uint32_t y = 0; y < H; ++y) {
-    const uint8_t* line = raw.data() + (size_t)y * (stride + 1); const int ft = line[0];
-    for (size_t i = 0; i < stride; ++i) {
-      const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-      int pr;
-      switch (ft) {
-        case 0: pr = 0; break; case 1: pr = a; break; case 2: pr = b; break; case 3: pr = (a + b) >> 1; break;
-        case 4: { const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c); pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
-        default: return fail(SCN_ERR_FORMAT, "bad PNG filter");
+  if (zlib_inflate(idat.data(), idat.size(), raw, need) || raw.size() < need) return fail(SCN_ERR_FORMAT, "corrupt PNG data");
+  // one (sub-)image: undo the row filters, expand to RGB8, write pixel (x, y) to (x0 + x*dx, y0 + y*dy)
+  auto run_pass = [&](const uint8_t* src, uint32_t pw, uint32_t ph, uint32_t x0, uint32_t y0, uint32_t dx, uint32_t dy) -> int {
+    const size_t stride = ((size_t)pw * ch * depth + 7) / 8;
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    for (uint32_t y = 0; y < ph; ++y) {
+      const uint8_t* line = src + (size_t)y * (stride + 1); const int ft = line[0];
+      for (size_t i = 0; i < stride; ++i) {
+        const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+        int pr;
+        switch (ft) {
+          case 0: pr = 0; break; case 1: pr = a; break; case 2: pr = b; break; case 3: pr = (a + b) >> 1; break;
+          case 4: { const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c); pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
+          default: return fail(SCN_ERR_FORMAT, "bad PNG filter");
+        }
+        cur[i] = (uint8_t)(line[1 + i] + pr);
       }
-      cur[i] = (uint8_t)(line[1 + i] + pr);
+      uint8_t* orow = out + (size_t)(y0 + y * dy) * W * 3;
+      for (uint32_t x = 0; x < pw; ++x) {
+        auto sample = [&](int k) -> int {                       // k-th channel of pixel x as an 8-bit value
+          if (depth == 8) return cur[(size_t)x * ch + k];
+          const size_t bit = (size_t)x * depth; const int v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+          return ctype == 3 ? v : v * (255 / ((1 << depth) - 1));
+        };
+        uint8_t* o = orow + (size_t)(x0 + x * dx) * 3;
+        if (ctype == 3) { const int idx = sample(0); for (int k = 0; k < 3; ++k) o[k] = (size_t)(3 * idx + k) < pal.size() ? pal[3 * idx + k] : 0; }
+        else if (ch <= 2) { const uint8_t g = (uint8_t)sample(0); o[0] = o[1] = o[2] = g; }
+        else for (int k = 0; k < 3; ++k) o[k] = (uint8_t)sample(k);
+      }
+      prev.swap(cur);
     }
-    uint8_t* o = out + (size_t)y * W * 3;
-    for (uint32_t x = 0; x < W; ++x) {
-      auto sample = [&](int k) -> int {                       // k-th channel of pixel x as an 8-bit value
-        if (depth == 8) return cur[(size_t)x * ch + k];
-        const size_t bit = (size_t)x * depth; const int v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
-        return ctype == 3 ? v : v * (255 / ((1 << depth) - 1));
-      };
-      if (ctype == 3) { const int idx = sample(0); for (int k = 0; k < 3; ++k) o[3 * x + k] = (size_t)(3 * idx + k) < pal.size() ? pal[3 * idx + k] : 0; }
-      else if (ch <= 2) { const uint8_t g = (uint8_t)sample(0); o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = g; }
-      else for (int k = 0; k < 3; ++k) o[3 * x + k] = (uint8_t)sample(k);
-    }
-    prev.swap(cur);
+    return SCN_OK;
+  };
+  if (!interlace) return run_pass(raw.data(), W, H, 0, 0, 1, 1);
+  size_t off = 0;
+  for (int p = 0; p < 7; ++p) {
+    const uint32_t pw = (W - xorig[p] + xspc[p] - 1) / xspc[p], ph = (H - yorig[p] + yspc[p] - 1) / yspc[p];
+    if (!pw || !ph) continue;
+    if (int rc = run_pass(raw.data() + off, pw, ph, xorig[p], yorig[p], xspc[p], yspc[p])) return rc;
+    off += pass_bytes(pw, ph);
   }
   return SCN_OK;
 }
