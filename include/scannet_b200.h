@@ -124,6 +124,15 @@ int  scn_sens_frame_depth_u16(const scn_sens* s, uint64_t frame, uint16_t* out);
 int  scn_sens_frame_color_rgb8(const scn_sens* s, uint64_t frame, uint8_t* out);
 /* raw compressed payloads (pointers into the handle; valid until scn_sens_close) */
 int  scn_sens_frame_payload(const scn_sens* s, uint64_t frame, const uint8_t** color, const uint8_t** depth);
+/* Read-ahead decoder: the counterpart of SensorData::RGBDFrameCacheRead (sensorData.h:1717-1835), which the reconstruction
+ * binaries pull frames from.  Background threads (the reference has one; n_threads <= 0 picks min(8, cores)) decode depth and
+ * colour of up to cache_size frames ahead of the consumer, in stream order.  scn_sens_cache_next copies the next frame into the
+ * caller's buffers (either may be NULL) and returns 1, returns 0 after the last frame, negative on a decode error of that
+ * frame.  The scn_sens handle must outlive the cache and must not be modified while it exists. */
+typedef struct scn_sens_cache scn_sens_cache;
+int  scn_sens_cache_create(const scn_sens* s, uint32_t cache_size, int n_threads, scn_sens_cache** out);
+int  scn_sens_cache_next(scn_sens_cache* c, uint16_t* depth_out, uint8_t* color_rgb8_out, uint64_t* ts_depth, uint64_t* ts_color);
+void scn_sens_cache_destroy(scn_sens_cache* c);
 /* replace a frame's pose (as `recons` writes optimised trajectories back, zParametersScanNet.txt:5) */
 int  scn_sens_set_pose(scn_sens* s, uint64_t frame, const float cam2world[16]);
 int  scn_sens_save(const scn_sens* s, const char* path);

@@ -19,6 +19,9 @@
 #include <limits>
 #include <sstream>
 #include <string>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "scn_common.h"
@@ -446,6 +449,73 @@ int scn_sens_frame_payload(const scn_sens* s, uint64_t i, const uint8_t** color,
   if (color) *color = s->frames[i].color.data();
   if (depth) *depth = s->frames[i].depth.data();
   return SCN_OK;
+}
+
+// ------------------------------------------------------------------------------ read-ahead cache (RGBDFrameCacheRead)
+struct scn_sens_cache {
+  struct Slot { std::vector<uint16_t> depth; std::vector<uint8_t> color; int rc = 0; std::string err; bool ready = false; };
+  const scn_sens* s = nullptr;
+  std::vector<Slot> slots;
+  std::vector<std::thread> workers;
+  std::mutex m; std::condition_variable cv_ready, cv_space;
+  uint64_t next_claim = 0, next_out = 0; bool stop = false;
+  void work() {
+    for (;;) {
+      uint64_t i;
+      {
+        std::unique_lock<std::mutex> l(m);
+        cv_space.wait(l, [&]() { return stop || next_claim >= s->frames.size() || next_claim < next_out + slots.size(); });
+        if (stop || next_claim >= s->frames.size()) return;
+        i = next_claim++;
+      }
+      Slot& sl = slots[i % slots.size()];                      // free: the consumer has passed frame i - slots.size()
+      sl.depth.resize((size_t)s->dw * s->dh); sl.color.resize((size_t)s->cw * s->ch * 3);
+      int rc = scn_sens_frame_depth_u16(s, i, sl.depth.data());
+      if (!rc && s->color_comp >= 0 && !s->frames[i].color.empty()) rc = scn_sens_frame_color_rgb8(s, i, sl.color.data());
+      { std::lock_guard<std::mutex> l(m); sl.rc = rc; if (rc) sl.err = scn_last_error(); sl.ready = true; }
+      cv_ready.notify_all();
+    }
+  }
+};
+
+int scn_sens_cache_create(const scn_sens* s, uint32_t cache_size, int n_threads, scn_sens_cache** out) {
+  if (!s || !out || cache_size == 0) return scn::fail(SCN_ERR_ARG, "bad argument");
+  scn_sens_cache* c = new scn_sens_cache();
+  c->s = s; c->slots.resize(cache_size);
+  unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  nt = std::min<unsigned>(nt, cache_size);
+  for (unsigned t = 0; t < nt; ++t) c->workers.emplace_back([c]() { c->work(); });
+  *out = c;
+  return SCN_OK;
+}
+
+int scn_sens_cache_next(scn_sens_cache* c, uint16_t* depth_out, uint8_t* color_out, uint64_t* ts_depth, uint64_t* ts_color) {
+  if (!c) return scn::fail(SCN_ERR_ARG, "null handle");
+  std::unique_lock<std::mutex> l(c->m);
+  if (c->next_out >= c->s->frames.size()) return 0;
+  const uint64_t i = c->next_out;
+  scn_sens_cache::Slot& sl = c->slots[i % c->slots.size()];
+  c->cv_ready.wait(l, [&]() { return sl.ready && i < c->next_claim; });
+  const int rc = sl.rc;
+  if (rc) scn::fail(rc, "%s", sl.err.c_str());
+  else {
+    if (depth_out) memcpy(depth_out, sl.depth.data(), sl.depth.size() * 2);
+    if (color_out) memcpy(color_out, sl.color.data(), sl.color.size());
+    if (ts_depth) *ts_depth = c->s->frames[i].ts_depth;
+    if (ts_color) *ts_color = c->s->frames[i].ts_color;
+  }
+  sl.ready = false; ++c->next_out;
+  l.unlock();
+  c->cv_space.notify_all();
+  return rc ? rc : 1;
+}
+
+void scn_sens_cache_destroy(scn_sens_cache* c) {
+  if (!c) return;
+  { std::lock_guard<std::mutex> l(c->m); c->stop = true; }
+  c->cv_space.notify_all();
+  for (auto& t : c->workers) t.join();
+  delete c;
 }
 
 int scn_sens_set_pose(scn_sens* s, uint64_t i, const float cam2world[16]) {

@@ -71,6 +71,23 @@ class SensFile:
         """Frames [first, first+n) inflated on the GPU straight into device memory at `d_out_ptr` (n*H*W uint16)."""
         check(_L().scn_sens_decode_depth_device(self._h, C.c_uint64(first), C.c_uint32(n), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
+    def read_ahead(self, cache_size: int = 16, n_threads: int = 0):
+        """Iterator over (depth uint16 [H,W], colour uint8 [H,W,3], ts_depth, ts_color) decoded by background threads, in stream
+        order — the RGBDFrameCacheRead pattern (sensorData.h:1717-1835)."""
+        h = C.c_void_p()
+        check(_L().scn_sens_cache_create(self._h, C.c_uint32(cache_size), C.c_int(n_threads), C.byref(h)))
+        try:
+            while True:
+                d = np.zeros((self.info.depth_height, self.info.depth_width), np.uint16)
+                c = np.zeros((self.info.color_height, self.info.color_width, 3), np.uint8)
+                td = C.c_uint64(); tc = C.c_uint64()
+                rc = check(_L().scn_sens_cache_next(h, d.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), C.byref(td), C.byref(tc)))
+                if rc == 0:
+                    return
+                yield d, c, td.value, tc.value
+        finally:
+            _L().scn_sens_cache_destroy(h)
+
     def color(self, i: int) -> np.ndarray:
         out = np.zeros((self.info.color_height, self.info.color_width, 3), np.uint8)
         check(_L().scn_sens_frame_color_rgb8(self._h, C.c_uint64(i), out.ctypes.data_as(C.c_void_p)))

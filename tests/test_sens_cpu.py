@@ -304,3 +304,32 @@ def test_interlaced_png_matches_stb(tmp_path, built, wh, kind):
         assert (ours == ref).all(), (kind, filt)
     ours, ref = _decode_both(tmp_path, _png(img.astype(np.uint8), False, depth, ct, pal, 1), W, H, 1)       # and the plain layout through the same writer
     assert (ours == ref).all()
+
+
+@pytest.mark.parametrize("cache,threads", [(1, 1), (3, 2), (16, 0), (64, 8)])
+def test_read_ahead_cache_returns_the_stream_in_order(stream, cache, threads):
+    """RGBDFrameCacheRead counterpart: same frames as the random-access decode, in order, for any cache size / thread count"""
+    p, D, Cc, P, K = stream
+    s = SensFile(p)
+    got = list(s.read_ahead(cache, threads))
+    assert len(got) == s.n_frames
+    for i, (d, c, td, tc) in enumerate(got):
+        assert (d == s.depth(i)).all() and (c == s.color(i)).all()
+        assert (td, tc) == (s.frame_meta(i)[2], s.frame_meta(i)[1])
+
+
+def test_read_ahead_cache_early_exit_and_errors(stream, tmp_path):
+    from scannet_b200 import ScnError
+    p = stream[0]
+    s = SensFile(p)
+    it = s.read_ahead(2, 2); next(it); it.close()                      # destroyed while workers are mid-stream
+    raw = bytearray(open(p, "rb").read())
+    # corrupt the zlib header of the LAST frame's depth payload (the file ends: ..., color payload, depth payload, u64 numIMU = 0)
+    n_depth = s.frame_meta(s.n_frames - 1)[4]
+    raw[len(raw) - 8 - n_depth] ^= 0xFF
+    q = tmp_path / "bad.sens"; q.write_bytes(bytes(raw))
+    t = SensFile(str(q)); it = t.read_ahead(4, 2)
+    for _ in range(t.n_frames - 1):
+        next(it)
+    with pytest.raises(ScnError, match="corrupt zlib depth stream"):
+        next(it)
