@@ -341,7 +341,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
               k += (fa >> 4) & 15;
               const int used = fa & 15;
               br.buf <<= used; br.cnt -= used;
-              data[kZig[k++ & 63]] = (short)((fa >> 8) << shift);
+              data[kZig[k++]] = (short)((fa >> 8) << shift);
             } else {
               const int rs = br.decode(ha);
               if (rs < 0) return false;
@@ -349,7 +349,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
               if (sz == 0) {
                 if (r < 15) { eob_run = 1 << r; if (r) eob_run += br.get(r); --eob_run; break; }
                 k += 16;
-              } else { k += r; data[kZig[k++ & 63]] = (short)(extend(br.get(sz), sz) << shift); }
+              } else { k += r; data[kZig[k++]] = (short)(extend(br.get(sz), sz) << shift); }
             }
           } while (k <= spec_end);
         } else {

@@ -347,6 +347,9 @@ int scn_sens_open(const char* path, scn_sens** out) {
   if (!path || !out) return scn::fail(SCN_ERR_ARG, "null argument");
   std::ifstream in(path, std::ios::binary);
   if (!in.is_open()) return scn::fail(SCN_ERR_IO, "could not open file %s", path);         // sensorData.h:1253-1255
+  in.seekg(0, std::ios::end); const uint64_t file_size = (uint64_t)std::max<std::streamoff>(in.tellg(), 0); in.seekg(0, std::ios::beg);
+  // every count / size field is checked against what the file can still hold before anything is allocated for it
+  auto left = [&]() { const std::streamoff p = in.tellg(); return p < 0 ? (uint64_t)0 : file_size - std::min<uint64_t>(file_size, (uint64_t)p); };
   scn_sens* s = new scn_sens();
   auto bail = [&](int code, const char* msg) { delete s; return scn::fail(code, "%s: %s", path, msg); };
   if (!rd(in, s->version)) return bail(SCN_ERR_FORMAT, "truncated header");
@@ -355,7 +358,7 @@ int scn_sens_open(const char* path, scn_sens** out) {
     return scn::fail(SCN_ERR_FORMAT, "Invalid file version -- found %u but expectd 4", v);
   }
   uint64_t slen = 0;
-  if (!rd(in, slen) || slen > (1u << 20)) return bail(SCN_ERR_FORMAT, "bad sensor name length");
+  if (!rd(in, slen) || slen > (1u << 20) || slen > left()) return bail(SCN_ERR_FORMAT, "bad sensor name length");
   s->sensor_name.resize(slen);
   in.read(&s->sensor_name[0], (std::streamsize)slen);
   in.read((char*)s->color_intr, 64); in.read((char*)s->color_extr, 64);
@@ -364,7 +367,7 @@ int scn_sens_open(const char* path, scn_sens** out) {
   rd(in, s->cw); rd(in, s->ch); rd(in, s->dw); rd(in, s->dh); rd(in, s->depth_shift);
   uint64_t nf = 0;
   if (!rd(in, nf)) return bail(SCN_ERR_FORMAT, "truncated header");
-  if (nf > (1ull << 32)) return bail(SCN_ERR_FORMAT, "implausible frame count");
+  if (nf > (1ull << 32) || nf > left() / 96) return bail(SCN_ERR_FORMAT, "implausible frame count");          // 96 = pose + 2 stamps + 2 sizes
   s->frames.resize(nf);
   for (uint64_t i = 0; i < nf; ++i) {
     scn_sens_frame& f = s->frames[i];
@@ -372,13 +375,15 @@ int scn_sens_open(const char* path, scn_sens** out) {
     in.read((char*)f.cam2world, 64);
     if (!rd(in, f.ts_color) || !rd(in, f.ts_depth) || !rd(in, cb) || !rd(in, db)) return bail(SCN_ERR_FORMAT, "truncated frame header");
     if (cb > kMaxPayload || db > kMaxPayload) return bail(SCN_ERR_FORMAT, "implausible payload size");
+    if (cb + db > left()) return bail(SCN_ERR_FORMAT, "truncated frame payload");
     f.color.resize(cb); f.depth.resize(db);
     if (cb) in.read((char*)f.color.data(), (std::streamsize)cb);
     if (db) in.read((char*)f.depth.data(), (std::streamsize)db);
     if (!in) return bail(SCN_ERR_FORMAT, "truncated frame payload");
   }
   uint64_t ni = 0;
-  if (rd(in, ni) && ni > 0 && ni < (1ull << 32)) {
+  if (rd(in, ni) && ni > 0) {
+    if (ni >= (1ull << 32) || ni > left() / 128) return bail(SCN_ERR_FORMAT, "truncated IMU frames");
     s->imu.resize(ni);
     for (uint64_t i = 0; i < ni; ++i) { s->imu[i].resize(128); in.read((char*)s->imu[i].data(), 128); if (!in) return bail(SCN_ERR_FORMAT, "truncated IMU frames"); }
   }
