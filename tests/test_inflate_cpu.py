@@ -74,3 +74,32 @@ def test_fuzz_against_zlib(built):
         co = zlib.compressobj(level, zlib.DEFLATED, wbits, memlevel, strategy)
         assert sens.inflate_host(co.compress(raw) + co.flush(), len(raw)) == raw
     run()
+
+
+def test_corrupted_streams_never_escape_the_output_buffer(built):
+    """6000 mutated zlib streams (all block types) through the host build of the GPU decoder source: each call returns bytes or
+    raises ScnError, and a canary behind the output buffer stays intact (the kernel runs the same code with the same bounds)."""
+    import ctypes as C
+    from scannet_b200._lib import lib
+    L = lib()
+    L.scn_inflate_host.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    rng = np.random.default_rng(11)
+    raws = [payloads()[k] for k in ("depth", "period3", "noise")]
+    seeds = [(f(r), len(r)) for r in raws for f in encoders().values()]
+    buf = np.zeros(max(n for _, n in seeds) + 64, np.uint8)
+    for it in range(6000):
+        comp, cap = seeds[it % len(seeds)]
+        b = bytearray(comp)
+        for _ in range(int(rng.integers(1, 5))):
+            p = int(rng.integers(2, len(b)))
+            op = int(rng.integers(0, 4))
+            if op == 0: b[p] ^= 1 << int(rng.integers(0, 8))
+            elif op == 1: b[p] = int(rng.integers(0, 256))
+            elif op == 2: del b[p:p + int(rng.integers(1, 9))]
+            else: b = b[:p]
+            if len(b) < 3: break
+        buf[cap:cap + 64] = 0xA5
+        n = C.c_size_t()
+        rc = L.scn_inflate_host(bytes(b), len(b), buf.ctypes.data, cap, C.byref(n))
+        assert rc in (0, -4), rc                                            # SCN_OK or SCN_ERR_FORMAT
+        assert n.value <= cap and (buf[cap:cap + 64] == 0xA5).all()
