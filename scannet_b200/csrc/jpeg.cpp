@@ -102,6 +102,13 @@ struct Bits {
 inline int extend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
 inline uint8_t clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x; }
 
+// AVX2 clones of the two hot loops, picked at load time.  (SCN_NO_TARGET_CLONES: ThreadSanitizer builds — the ifunc
+// resolver would run before the sanitizer runtime is up.)
+#ifdef SCN_NO_TARGET_CLONES
+#define SCN_CLONES
+#else
+#define SCN_CLONES __attribute__((target_clones("avx2", "default")))
+#endif
 #define F2F(x) ((int)(((x) * 4096 + 0.5)))
 #define IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                      \
   int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                            \
@@ -121,7 +128,7 @@ inline uint8_t clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (
   p3 = p3 * F2F(-1.961570560f); p4 = p4 * F2F(-0.390180644f);                        \
   t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
 
-__attribute__((target_clones("avx2", "default")))
+SCN_CLONES
 void idct8x8(uint8_t* out, int stride, const short* d) {
   int val[64];
   for (int i = 0; i < 8; ++i) {
@@ -181,7 +188,7 @@ inline void ycc_to_rgb(uint8_t* out, int y, int cbv, int crv) {
   out[0] = clamp8(r); out[1] = clamp8(g); out[2] = clamp8(b);
 }
 
-__attribute__((target_clones("avx2", "default")))
+SCN_CLONES
 void ycc_row_to_rgb(uint8_t* o, const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int W) {
   for (int i = 0; i < W; ++i) ycc_to_rgb(o + 3 * i, y[i], cb[i], cr[i]);
 }

@@ -55,7 +55,30 @@ static std::vector<uint8_t> mutate(const std::vector<uint8_t>& seed, size_t skip
 }
 
 int main(int argc, char** argv) {
-  if (argc < 5) { fprintf(stderr, "usage: host_fuzz <kind: sens|mesh|segs> <seed file> <work dir> <iterations>\n"); return 2; }
+  if (argc >= 3 && std::string(argv[1]) == "cache") {
+    // read-ahead cache stress (built with ThreadSanitizer by tests/test_fuzz_cpu.py): many cache sizes / thread counts, early destroys
+    scn_sens* s = nullptr;
+    if (scn_sens_open(argv[2], &s)) { fprintf(stderr, "%s\n", scn_last_error()); return 2; }
+    scn_sens_info_t in; scn_sens_info(s, &in);
+    std::vector<uint16_t> dep((size_t)in.depth_width * in.depth_height), ref(dep.size()); std::vector<uint8_t> col((size_t)in.color_width * in.color_height * 3);
+    long frames = 0;
+    for (int round = 0; round < 24; ++round) {
+      scn_sens_cache* c = nullptr;
+      if (scn_sens_cache_create(s, 1 + round % 7, 1 + round % 5, &c)) return 3;
+      const uint64_t stop_at = round % 3 == 2 ? in.n_frames / 2 : in.n_frames + 1;      // every third round abandons the stream half way
+      uint64_t i = 0; uint64_t td, tc;
+      while (i < stop_at && scn_sens_cache_next(c, dep.data(), col.data(), &td, &tc) == 1) {
+        scn_sens_frame_depth_u16(s, i, ref.data());
+        if (memcmp(ref.data(), dep.data(), dep.size() * 2)) { fprintf(stderr, "frame %llu differs\n", (unsigned long long)i); return 4; }
+        ++i; ++frames;
+      }
+      scn_sens_cache_destroy(c);
+    }
+    scn_sens_close(s);
+    printf("cache: %ld frames delivered in order\n", frames);
+    return 0;
+  }
+  if (argc < 5) { fprintf(stderr, "usage: host_fuzz <kind: sens|mesh|segs> <seed file> <work dir> <iterations>  |  host_fuzz cache <file.sens>\n"); return 2; }
   const std::string kind = argv[1], work = argv[3]; const int iters = atoi(argv[4]);
   const std::vector<uint8_t> seed = slurp(argv[2]);
   if (seed.empty()) { fprintf(stderr, "empty seed\n"); return 2; }

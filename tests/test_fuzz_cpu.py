@@ -76,3 +76,20 @@ def test_segs_json_reader(fuzzer):
     seed = str(d / "s.segs.json")
     json.dump({"params": {"kThresh": 0.01, "segMinVerts": 20}, "sceneId": "/x", "segIndices": list(range(0, 3000, 7)) * 3}, open(seed, "w"), separators=(",", ":"))
     assert "4000 inputs" in run(exe, "segs", seed, d, 4000)
+
+
+def test_read_ahead_cache_under_thread_sanitizer(tmp_path):
+    """the RGBDFrameCacheRead counterpart (scn_sens_cache_*) built with -fsanitize=thread: producers, consumer and early destruction"""
+    import cv2
+    exe = str(tmp_path / "host_tsan")
+    srcs = [os.path.join(ROOT, "tests", "fuzz", "host_fuzz.cpp")] + [os.path.join(ROOT, "scannet_b200", "csrc", f) for f in ("jpeg.cpp", "sens.cpp", "mesh_io.cpp")]
+    r = subprocess.run([CXX, "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-DSCN_NO_TARGET_CLONES", "-o", exe] + srcs + ["-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in (r.stderr or "").lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr[-2000:]
+    D, C, P, K = synth.make_frames(12, seed=3, width=64, height=48, loop_frames=40, noise_mm=1.0)
+    seed = str(tmp_path / "c.sens")
+    synth.write_sens(seed, D, C, P, K, depth_comp=1, color_comp=2, jpeg_encoder=lambda x: cv2.imencode(".jpg", x[:, :, ::-1])[1].tobytes())
+    r = subprocess.run([exe, "cache", seed], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (r.stdout[-300:], r.stderr[-3000:])
+    assert "frames delivered in order" in r.stdout
