@@ -333,3 +333,46 @@ def test_read_ahead_cache_early_exit_and_errors(stream, tmp_path):
         next(it)
     with pytest.raises(ScnError, match="corrupt zlib depth stream"):
         next(it)
+
+
+def test_simd_and_scalar_idct_give_the_same_bytes(tmp_path, built):
+    """the AVX2 IDCT against the scalar one (SCN_JPEG_SCALAR=1) on clean, extreme and corrupted JPEG payloads, in two child
+    processes (the switch is read once per process): same status and same pixels for every payload"""
+    import cv2, pickle, sys
+    rng = np.random.default_rng(9); W, H = 96, 72
+    payloads = []
+    for q in (100, 75, 20, 3):
+        for kind in ("noise", "smooth", "binary"):
+            if kind == "noise": img = rng.integers(0, 256, (H, W, 3))
+            elif kind == "smooth": xx, yy = np.meshgrid(np.arange(W), np.arange(H)); img = np.stack([xx, yy, np.zeros((H, W))], -1) * 2
+            else: img = (rng.integers(0, 2, (H, W, 3)) * 255)
+            for prog in (0, 1):
+                payloads.append(cv2.imencode(".jpg", img.astype(np.uint8), [int(cv2.IMWRITE_JPEG_QUALITY), q, int(cv2.IMWRITE_JPEG_PROGRESSIVE), prog])[1].tobytes())
+    clean = list(payloads)
+    for p in clean:                                              # corrupt the entropy-coded part: wild coefficients, early markers
+        for _ in range(6):
+            b = bytearray(p)
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(len(b) // 2, len(b) - 2))] = int(rng.integers(0, 255))
+            payloads.append(bytes(b))
+    D = np.full((len(payloads), 8, 8), 1000, np.uint16); P = np.tile(np.eye(4, dtype=np.float32), (len(payloads), 1, 1))
+    f = str(tmp_path / "many.sens"); it = iter(payloads)
+    synth.write_sens(f, D, np.zeros((len(payloads), H, W, 3), np.uint8), P, np.eye(4, dtype=np.float32), depth_comp=0, color_comp=2, jpeg_encoder=lambda x: next(it))
+    code = ("import sys, pickle, numpy as np; sys.path.insert(0, %r)\n"
+            "from scannet_b200.sens import SensFile\nfrom scannet_b200 import ScnError\n"
+            "s = SensFile(%r); out = []\n"
+            "for i in range(s.n_frames):\n"
+            "    try: out.append(s.color(i).tobytes())\n"
+            "    except ScnError as e: out.append(str(e))\n"
+            "pickle.dump(out, open(sys.argv[1], 'wb'))\n") % (ROOT, f)
+    res = {}
+    for mode in ("simd", "scalar"):
+        o = str(tmp_path / (mode + ".pkl"))
+        env = dict(os.environ); env.pop("SCN_JPEG_SCALAR", None)
+        if mode == "scalar": env["SCN_JPEG_SCALAR"] = "1"
+        r = subprocess.run([sys.executable, "-c", code, o], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        res[mode] = pickle.load(open(o, "rb"))
+    assert len(res["simd"]) == len(payloads)
+    assert sum(isinstance(x, bytes) for x in res["simd"]) >= len(clean)
+    assert res["simd"] == res["scalar"]
