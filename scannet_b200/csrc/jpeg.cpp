@@ -203,11 +203,18 @@ __attribute__((target("avx2"))) static void idct8x8_avx2(uint8_t* out, int strid
 }
 #endif
 
+inline bool use_avx2() {
+#if defined(__x86_64__)
+  static const bool simd = __builtin_cpu_supports("avx2") && !getenv("SCN_JPEG_SCALAR");      // the env switch exists for the A/B parity test
+  return simd;
+#else
+  return false;
+#endif
+}
 void idct8x8_scalar(uint8_t* out, int stride, const short* d);
 void idct8x8(uint8_t* out, int stride, const short* d) {
 #if defined(__x86_64__)
-  static const bool simd = __builtin_cpu_supports("avx2") && !getenv("SCN_JPEG_SCALAR");      // the env switch exists for the A/B parity test
-  if (simd) { idct8x8_avx2(out, stride, d); return; }
+  if (use_avx2()) { idct8x8_avx2(out, stride, d); return; }
 #endif
   idct8x8_scalar(out, stride, d);
 }
@@ -248,11 +255,37 @@ const uint8_t* up_v2(uint8_t* out, const uint8_t* nr, const uint8_t* fr, int w) 
   for (int i = 0; i < w; ++i) out[i] = (uint8_t)((3 * nr[i] + fr[i] + 2) >> 2);
   return out;
 }
+#if defined(__x86_64__)
+// out[2j] = (3 t[j] + t[j-1] + 8) >> 4, out[2j+1] = (3 t[j] + t[j+1] + 8) >> 4 with t = 3*near + far, for 16 values of j at a time
+// in 16-bit lanes (t <= 1020, sums <= 4088); the pair (even, odd) of one j is one little-endian 16-bit lane of the output.
+__attribute__((target("avx2"))) static int up_hv2_avx2(uint8_t* out, const uint8_t* nr, const uint8_t* fr, int w) {
+  int j = 1;
+  const __m256i three = _mm256_set1_epi16(3), eight = _mm256_set1_epi16(8);
+#define SCN_TVEC(k) _mm256_add_epi16(_mm256_mullo_epi16(_mm256_cvtepu8_epi16(_mm_loadu_si128((const __m128i*)(nr + (k)))), three), \
+                                     _mm256_cvtepu8_epi16(_mm_loadu_si128((const __m128i*)(fr + (k)))))
+  for (; j + 17 <= w; j += 16) {                                  // needs t[j-1 .. j+16]
+    const __m256i t = SCN_TVEC(j), tm = SCN_TVEC(j - 1), tp = SCN_TVEC(j + 1);
+    const __m256i t3 = _mm256_add_epi16(_mm256_mullo_epi16(t, three), eight);
+    const __m256i ev = _mm256_srli_epi16(_mm256_add_epi16(t3, tm), 4), od = _mm256_srli_epi16(_mm256_add_epi16(t3, tp), 4);
+    _mm256_storeu_si256((__m256i*)(out + 2 * j), _mm256_or_si256(ev, _mm256_slli_epi16(od, 8)));
+  }
+#undef SCN_TVEC
+  return j;                                                       // first j not done
+}
+#endif
 const uint8_t* up_hv2(uint8_t* out, const uint8_t* nr, const uint8_t* fr, int w) {
   if (w == 1) { out[0] = out[1] = (uint8_t)((3 * nr[0] + fr[0] + 2) >> 2); return out; }
   int t1 = 3 * nr[0] + fr[0], t0;
   out[0] = (uint8_t)((t1 + 2) >> 2);
-  for (int i = 1; i < w; ++i) { t0 = t1; t1 = 3 * nr[i] + fr[i]; out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4); out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4); }
+  int i = 1;
+#if defined(__x86_64__)
+  if (use_avx2() && w >= 18) {
+    out[1] = (uint8_t)((3 * t1 + (3 * nr[1] + fr[1]) + 8) >> 4);   // out[2*0+1], the odd sample of j = 0
+    i = up_hv2_avx2(out, nr, fr, w);                              // wrote out[2 .. 2i-1]
+    t1 = 3 * nr[i - 1] + fr[i - 1];
+  }
+#endif
+  for (; i < w; ++i) { t0 = t1; t1 = 3 * nr[i] + fr[i]; out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4); out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4); }
   out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
   return out;
 }
@@ -271,9 +304,36 @@ inline void ycc_to_rgb(uint8_t* out, int y, int cbv, int crv) {
   out[0] = clamp8(r); out[1] = clamp8(g); out[2] = clamp8(b);
 }
 
-SCN_CLONES
+#if defined(__x86_64__)
+// eight pixels per step in 32-bit lanes, the same fixed-point arithmetic; saturating packs == clamp8; a byte shuffle interleaves
+__attribute__((target("avx2"))) static int ycc_row_to_rgb_avx2(uint8_t* o, const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int W) {
+  const __m256i c128 = _mm256_set1_epi32(128), half = _mm256_set1_epi32(1 << 19), mask = _mm256_set1_epi32((int)0xffff0000);
+  const __m256i k_r = _mm256_set1_epi32(FIX20(1.40200f)), k_g1 = _mm256_set1_epi32(-FIX20(0.71414f)), k_g2 = _mm256_set1_epi32(-FIX20(0.34414f)),
+                k_b = _mm256_set1_epi32(FIX20(1.77200f));
+  const __m256i shuf = _mm256_setr_epi8(0, 4, 8, 1, 5, 9, 2, 6, 10, 3, 7, 11, -1, -1, -1, -1, 0, 4, 8, 1, 5, 9, 2, 6, 10, 3, 7, 11, -1, -1, -1, -1);
+  int i = 0;
+  for (; i + 10 <= W; i += 8) {                                   // the two 16-byte stores cover 28 bytes from 3*i: stay inside the row
+    const __m256i yy = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(y + i)));
+    const __m256i b_ = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(cb + i))), c128);
+    const __m256i r_ = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(cr + i))), c128);
+    const __m256i yf = _mm256_add_epi32(_mm256_slli_epi32(yy, 20), half);
+    const __m256i r = _mm256_srai_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(r_, k_r)), 20);
+    const __m256i g = _mm256_srai_epi32(_mm256_add_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(r_, k_g1)), _mm256_and_si256(_mm256_mullo_epi32(b_, k_g2), mask)), 20);
+    const __m256i b = _mm256_srai_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(b_, k_b)), 20);
+    const __m256i rg = _mm256_packs_epi32(r, g), bb = _mm256_packs_epi32(b, b);         // per half: r0-3 g0-3 | b0-3 b0-3
+    const __m256i px = _mm256_shuffle_epi8(_mm256_packus_epi16(rg, bb), shuf);            // per half: r0 g0 b0 r1 g1 b1 ... b3 x x x x
+    _mm_storeu_si128((__m128i*)(o + 3 * i), _mm256_castsi256_si128(px));
+    _mm_storeu_si128((__m128i*)(o + 3 * i + 12), _mm256_extracti128_si256(px, 1));
+  }
+  return i;
+}
+#endif
 void ycc_row_to_rgb(uint8_t* o, const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int W) {
-  for (int i = 0; i < W; ++i) ycc_to_rgb(o + 3 * i, y[i], cb[i], cr[i]);
+  int i = 0;
+#if defined(__x86_64__)
+  if (use_avx2()) i = ycc_row_to_rgb_avx2(o, y, cb, cr, W);
+#endif
+  for (; i < W; ++i) ycc_to_rgb(o + 3 * i, y[i], cb[i], cr[i]);
 }
 
 }  // namespace
