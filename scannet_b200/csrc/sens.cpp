@@ -49,7 +49,14 @@ struct BitIn {
   BitIn(const uint8_t* d, size_t n) : p(d), end(d + n) {}
   // past the end zero bytes are fed (the look-ahead may legitimately run a few bytes over); a stream that actually
   // consumes them is truncated: `bad` is raised once more than one reservoir of padding has been supplied
-  inline void fill() { while (cnt <= 56) { if (p < end) buf |= (uint64_t)(*p++) << cnt; else if (++pad > 16) bad = true; cnt += 8; } }
+  inline void fill() {
+    if (end - p >= 8) {                                       // one unaligned 8-byte load tops the reservoir up to 56..63 bits
+      uint64_t v; memcpy(&v, p, 8);
+      buf |= v << cnt; p += (63 - cnt) >> 3; cnt |= 56;
+      return;
+    }
+    while (cnt <= 56) { if (p < end) buf |= (uint64_t)(*p++) << cnt; else if (++pad > 16) bad = true; cnt += 8; }
+  }
   inline uint32_t peek(int k) { if (cnt < k) fill(); return (uint32_t)(buf & ((1ull << k) - 1)); }
   inline void drop(int k) { buf >>= k; cnt -= k; }
   inline uint32_t bits(int k) { if (k == 0) return 0; const uint32_t v = peek(k); drop(k); return v; }
@@ -104,7 +111,7 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
   if (n < 6) return -1;
   if ((src[0] & 0x0F) != 8 || ((src[0] << 8) | src[1]) % 31 != 0 || (src[1] & 0x20)) return -1;
   BitIn br(src + 2, n - 2);
-  out.resize(size_hint ? size_hint : std::max<size_t>(n * 4, 1 << 16));
+  out.resize((size_hint ? size_hint : std::max<size_t>(n * 4, 1 << 16)) + 320);
   size_t op = 0;
   auto ensure = [&](size_t extra) { if (op + extra > out.size()) out.resize(std::max(out.size() * 2, op + extra)); };
   static thread_local Huff lit, dist;
@@ -149,9 +156,10 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
         if (!lit.build(lens, nlen) || !dist.build(lens + nlen, ndist)) return -1;
       }
       for (;;) {
+        if (op + 300 > out.size()) ensure(300);               // room for a literal or the longest match plus the copy overshoot
         const int sym = lit.decode(br);
         if (sym < 0) return -1;
-        if (sym < 256) { if (op == out.size()) { if (br.bad) return -1; ensure(1); } out[op++] = (uint8_t)sym; }
+        if (sym < 256) { out[op++] = (uint8_t)sym; }
         else if (sym == 256) break;
         else {
           const int li = sym - 257;
@@ -161,9 +169,10 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
           if (ds < 0 || ds >= 30) return -1;
           const size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
           if (d > op) return -1;
-          ensure(len);
           uint8_t* dst = out.data() + op; const uint8_t* from = dst - d;
-          if (d >= len) memcpy(dst, from, len); else for (size_t i = 0; i < len; ++i) dst[i] = from[i];
+          if (d >= 8) {                                         // 8 bytes at a time; may write up to 7 bytes past the match (slack above)
+            for (size_t i = 0; i < len; i += 8) { uint64_t v; memcpy(&v, from + i, 8); memcpy(dst + i, &v, 8); }
+          } else for (size_t i = 0; i < len; ++i) dst[i] = from[i];
           op += len;
         }
         if (br.bad) return -1;
