@@ -44,6 +44,14 @@ const uint8_t kLenExtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5
 const uint16_t kDistBase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
 const uint8_t kDistExtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
 
+#define LP(b, e) ((uint32_t)(b) | ((uint32_t)(e) << 16))
+const uint32_t kLenPacked[29] = {LP(3,0),LP(4,0),LP(5,0),LP(6,0),LP(7,0),LP(8,0),LP(9,0),LP(10,0),LP(11,1),LP(13,1),LP(15,1),LP(17,1),LP(19,2),LP(23,2),LP(27,2),LP(31,2),
+                                 LP(35,3),LP(43,3),LP(51,3),LP(59,3),LP(67,4),LP(83,4),LP(99,4),LP(115,4),LP(131,5),LP(163,5),LP(195,5),LP(227,5),LP(258,0)};
+const uint32_t kDistPacked[30] = {LP(1,0),LP(2,0),LP(3,0),LP(4,0),LP(5,1),LP(7,1),LP(9,2),LP(13,2),LP(17,3),LP(25,3),LP(33,4),LP(49,4),LP(65,5),LP(97,5),LP(129,6),LP(193,6),
+                                  LP(257,7),LP(385,7),LP(513,8),LP(769,8),LP(1025,9),LP(1537,9),LP(2049,10),LP(3073,10),LP(4097,11),LP(6145,11),LP(8193,12),LP(12289,12),
+                                  LP(16385,13),LP(24577,13)};
+#undef LP
+
 struct BitIn {
   const uint8_t* p; const uint8_t* end; uint64_t buf = 0; int cnt = 0; int pad = 0; bool bad = false;
   BitIn(const uint8_t* d, size_t n) : p(d), end(d + n) {}
@@ -164,10 +172,13 @@ int scn::zlib_inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, s
         else {
           const int li = sym - 257;
           if (li >= 29) return -1;
-          const size_t len = kLenBase[li] + br.bits(kLenExtra[li]);
+          if (br.cnt < 48) br.fill();                           // length extra (5) + distance code (15) + distance extra (13) in one reservoir
+          const uint32_t le = kLenPacked[li];
+          const size_t len = (le & 0xFFFF) + (uint32_t)(br.buf & ((1u << (le >> 16)) - 1)); br.drop((int)(le >> 16));
           const int ds = dist.decode(br);
           if (ds < 0 || ds >= 30) return -1;
-          const size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
+          const uint32_t de = kDistPacked[ds];
+          const size_t d = (de & 0xFFFF) + (uint32_t)(br.buf & ((1u << (de >> 16)) - 1)); br.drop((int)(de >> 16));
           if (d > op) return -1;
           uint8_t* dst = out.data() + op; const uint8_t* from = dst - d;
           if (d >= 8) {                                         // 8 bytes at a time; may write up to 7 bytes past the match (slack above)
