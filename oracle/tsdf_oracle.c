@@ -136,8 +136,33 @@ void oracle_tsdf_destroy(oracle_tsdf* o) {
   free(o->touched); free(o->dm); free(o);
 }
 
+/* Per-thread set of block keys seen by step B (the touched SET does not depend on order, so the pixel walks
+ * may run on all host threads; the sets are merged into the table sequentially afterwards). */
+typedef struct { uint64_t* slot; uint64_t cap; uint64_t* list; uint64_t n, list_cap; } keyset;
+static void keyset_init(keyset* k) {
+  k->cap = 1 << 12; k->slot = (uint64_t*)malloc(k->cap * 8);
+  for (uint64_t i = 0; i < k->cap; ++i) k->slot[i] = EMPTY_KEY;
+  k->list_cap = 1 << 11; k->list = (uint64_t*)malloc(k->list_cap * 8); k->n = 0;
+}
+static void keyset_free(keyset* k) { free(k->slot); free(k->list); }
+static void keyset_add(keyset* k, int bx, int by, int bz) {
+  if (!key_ok(bx, by, bz)) return;
+  const uint64_t key = pack_key(bx, by, bz);
+  uint64_t s = mix64(key) & (k->cap - 1);
+  while (k->slot[s] != EMPTY_KEY) { if (k->slot[s] == key) return; s = (s + 1) & (k->cap - 1); }
+  k->slot[s] = key;
+  if (k->n == k->list_cap) { k->list_cap *= 2; k->list = (uint64_t*)realloc(k->list, k->list_cap * 8); }
+  k->list[k->n++] = key;
+  if (k->n * 2 > k->cap) {                                             /* grow + rehash */
+    const uint64_t nc = k->cap * 2; uint64_t* ns = (uint64_t*)malloc(nc * 8);
+    for (uint64_t i = 0; i < nc; ++i) ns[i] = EMPTY_KEY;
+    for (uint64_t i = 0; i < k->n; ++i) { uint64_t q = mix64(k->list[i]) & (nc - 1); while (ns[q] != EMPTY_KEY) q = (q + 1) & (nc - 1); ns[q] = k->list[i]; }
+    free(k->slot); k->slot = ns; k->cap = nc;
+  }
+}
+
 /* ---- spec step B: ray-band block allocation for one pixel ---------------------------- */
-static void alloc_pixel(oracle_tsdf* o, const float* T, float ifx, float ify, float cx, float cy,
+static void alloc_pixel(const oracle_tsdf* o, keyset* ks, const float* T, float ifx, float ify, float cx, float cy,
                         float inv_bs, int x, int y, float d) {
   const oracle_tsdf_params* p = &o->p;
   if (!(d >= p->depth_min && d <= p->depth_max)) return;
@@ -166,7 +191,7 @@ static void alloc_pixel(oracle_tsdf* o, const float* T, float ifx, float ify, fl
     else                  { step[i] = 0;  tmax[i] = INFINITY; tdelta[i] = INFINITY; }
   }
   for (int it = 0; it < 48; ++it) {
-    touch_block(o, cell[0], cell[1], cell[2]);
+    keyset_add(ks, cell[0], cell[1], cell[2]);
     if (cell[0] == end[0] && cell[1] == end[1] && cell[2] == end[2]) return;
     int ax;
     if (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) ax = 0; else if (tmax[1] <= tmax[2]) ax = 1; else ax = 2;
@@ -174,7 +199,7 @@ static void alloc_pixel(oracle_tsdf* o, const float* T, float ifx, float ify, fl
     cell[ax] += step[ax];
     tmax[ax] += tdelta[ax];
   }
-  touch_block(o, end[0], end[1], end[2]);
+  keyset_add(ks, end[0], end[1], end[2]);
 }
 
 /* ---- spec step C: integrate one block ------------------------------------------------ */
@@ -267,9 +292,29 @@ static int integrate_dm(oracle_tsdf* o, const uint8_t* rgb, const float* T, cons
   for (int i = 0; i < 9; ++i) Avs[i] = Rt[i] * p->voxel_size;
   const float inv_bs = 1.0f / (8.0f * p->voxel_size);
   const float ifx = 1.0f / fx, ify = 1.0f / fy;
-  /* step B (sequential: the touched SET does not depend on order) */
-  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
-    alloc_pixel(o, T, ifx, ify, cx, cy, inv_bs, x, y, o->dm[y * W + x]);
+  /* step B: pixel walks on all threads into per-thread key sets (the touched SET does not depend on order),
+   * then one sequential merge into the table */
+  {
+    const int nth = o->threads;
+    keyset* sets = (keyset*)malloc((size_t)nth * sizeof(keyset));
+    for (int i = 0; i < nth; ++i) keyset_init(&sets[i]);
+#pragma omp parallel num_threads(nth)
+    {
+#ifdef _OPENMP
+      keyset* ks = &sets[omp_get_thread_num()];
+#else
+      keyset* ks = &sets[0];
+#endif
+#pragma omp for schedule(static)
+      for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+        alloc_pixel(o, ks, T, ifx, ify, cx, cy, inv_bs, x, y, o->dm[y * W + x]);
+    }
+    for (int i = 0; i < nth; ++i) {
+      for (uint64_t j = 0; j < sets[i].n; ++j) { int32_t b[3]; unpack_key(sets[i].list[j], b); touch_block(o, b[0], b[1], b[2]); }
+      keyset_free(&sets[i]);
+    }
+    free(sets);
+  }
   /* step C (blocks are independent) */
   uint64_t n_upd = 0;
   const int64_t nt = (int64_t)o->n_touched;

@@ -66,6 +66,7 @@ void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vecto
   const size_t px = (size_t)in.depth_width * in.depth_height;
   c.n = n; c.rc = 0; c.poses.assign((size_t)n * 16, 0.f);
   std::atomic<uint32_t> next{0}; std::atomic<int> rc{0};
+  std::mutex err_m;
   auto work = [&]() {
     static thread_local std::vector<uint8_t> col;                               // kept per pool thread: no 1-4 MB allocation per chunk
     col.resize(use_color ? (size_t)in.color_width * in.color_height * 3 : 0);
@@ -80,12 +81,12 @@ void decode_chunk(const scn_sens* s, const scn_sens_info_t& in, const std::vecto
         if (!r) { uint8_t* o = c.rgb + (size_t)i * px * 3;
           for (size_t p = 0; p < px; ++p) { const int32_t q = lut[p]; if (q >= 0) { o[3 * p] = col[3 * q]; o[3 * p + 1] = col[3 * q + 1]; o[3 * p + 2] = col[3 * q + 2]; } else o[3 * p] = o[3 * p + 1] = o[3 * p + 2] = 0; } }
       }
-      if (r) { rc.store(r); }
+      // the error text is thread-local: capture it on the worker that failed
+      if (r) { std::lock_guard<std::mutex> l(err_m); if (!rc.load()) { c.err = scn_last_error(); rc.store(r); } }
     }
   };
   pool.run(work);
   c.rc = rc.load();
-  if (c.rc) c.err = scn_last_error();
 }
 
 }  // namespace
@@ -111,7 +112,7 @@ extern "C" int scn_fuse_main(int argc, const char** argv) {
   for (const std::string& f : params) if (scn_tsdf_params_from_file(f.c_str(), &p)) { fprintf(stderr, "%s\n", scn_last_error()); scn_sens_close(s); return 1; }
   p.width = in.depth_width; p.height = in.depth_height; p.depth_shift = in.depth_shift;   // integrate at the stream's depth resolution
   p.batch_frames = 16;
-  const bool use_color = in.color_compression == 0 || in.color_compression == 2;
+  const bool use_color = in.color_compression <= 2;           // raw, PNG, JPEG (sensorData.h:600-616)
   printf("fusing %s: %llu frames %ux%u, voxel %.4f m, truncation %.3f+%.3f*d\n", sens_path.c_str(), (unsigned long long)in.n_frames, in.depth_width,
          in.depth_height, p.voxel_size, p.trunc_base, p.trunc_scale);
   scn_tsdf* vol = nullptr;

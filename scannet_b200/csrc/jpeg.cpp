@@ -50,6 +50,13 @@ struct HuffTab {
   }
   bool build(const uint8_t* counts, const uint8_t* symbols, int nsym) {
     int code = 0, k = 0;
+    // validate before any table write (stb_image.h:1590-1615 rejects over-subscribed lengths before building its fast
+    // table): an over-subscribed code would index far outside fast[]
+    for (int l = 1, c = 0, tot = 0; l <= 16; ++l) {
+      c += counts[l - 1]; tot += counts[l - 1];
+      if (c > (1 << l) || tot > nsym || tot > 256) return false;
+      c <<= 1;
+    }
     for (int i = 0; i < (1 << kFastBits); ++i) fast[i] = 0xFFFF;
     for (int l = 1; l <= 16; ++l) {
       valptr[l] = k; mincode[l] = code;
@@ -391,6 +398,8 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
       if (sl < 6 || s[0] != 8) return fail(SCN_ERR_UNSUPPORTED, "only 8-bit JPEG");
       H = (s[1] << 8) | s[2]; W = (s[3] << 8) | s[4]; ncomp = s[5];
       if ((ncomp != 1 && ncomp != 3) || sl < (size_t)(6 + 3 * ncomp) || W == 0 || H == 0) return fail(SCN_ERR_FORMAT, "bad SOF");
+      // the container's header fixes the frame size: refuse before any plane is sized from in-stream values
+      if ((uint32_t)W != want_w || (uint32_t)H != want_h) return fail(SCN_ERR_FORMAT, "JPEG is %dx%d, header says %ux%u", W, H, want_w, want_h);
       for (int i = 0; i < ncomp; ++i) {
         comp[i].id = s[6 + 3 * i]; comp[i].h = s[7 + 3 * i] >> 4; comp[i].v = s[7 + 3 * i] & 15; comp[i].tq = s[8 + 3 * i];
         if (!comp[i].h || comp[i].h > 4 || !comp[i].v || comp[i].v > 4 || comp[i].tq > 3) return fail(SCN_ERR_FORMAT, "bad SOF component");
@@ -406,6 +415,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
       have_frame = true;
     } else if (m == 0xDA) {
       if (!have_frame) return fail(SCN_ERR_FORMAT, "SOS before SOF");
+      if (sl < 1) return fail(SCN_ERR_FORMAT, "bad SOS");
       const int ns = s[0];
       if (ns < 1 || ns > ncomp || sl < (size_t)(1 + 2 * ns + 3)) return fail(SCN_ERR_FORMAT, "bad SOS");
       int order[3];

@@ -104,10 +104,14 @@ int load_ply(const std::string& path, std::vector<float>& xyz, std::vector<uint3
       // fast path: fixed-size records
       bool fixed = true; size_t rec = 0;
       for (const PProp& p : el.props) { if (p.is_list) fixed = false; rec += psize(p.type); if (p.type == T_BAD) return scn::fail(SCN_ERR_FORMAT, "invalid ply property"); }
+      // bound the header's count by what the file can hold before any resize (overflow-safe: divide, never multiply)
+      size_t min_rec = 0;
+      for (const PProp& p : el.props) min_rec += p.is_list ? psize(p.list_type) : psize(p.type);
+      if (el.count > (n - std::min(pos, n)) / std::max<size_t>(min_rec, 1)) return scn::fail(SCN_ERR_FORMAT, "PLY body truncated");
       if (is_v) xyz.resize(el.count * 3);
       if (is_f) tri.reserve(el.count * 3);
       if (fixed) {
-        if (pos + rec * el.count > n) return scn::fail(SCN_ERR_FORMAT, "PLY body truncated");
+        if (rec * el.count > n - pos) return scn::fail(SCN_ERR_FORMAT, "PLY body truncated");
         if (is_v) {
           size_t ox = 0, oy = 0, oz = 0, o = 0;
           for (const PProp& p : el.props) { if (p.name == "x") ox = o; else if (p.name == "y") oy = o; else if (p.name == "z") oz = o; o += psize(p.type); }
@@ -156,6 +160,7 @@ int load_ply(const std::string& path, std::vector<float>& xyz, std::vector<uint3
     std::istringstream is(body);
     for (const PElem& el : elems) {
       const bool is_v = el.name == "vertex" && have_xyz, is_f = el.name == "face" && !face_prop.empty();
+      if (el.count > n - std::min(pos, n)) return scn::fail(SCN_ERR_FORMAT, "PLY body truncated");   // >= 1 byte per record
       if (is_v) xyz.resize(el.count * 3);
       for (size_t i = 0; i < el.count; ++i) for (const PProp& p : el.props) {
         if (!p.is_list) {
@@ -308,9 +313,12 @@ int scn_mesh_load(const char* path, float** xyz, uint64_t* n_verts, uint32_t** t
   const std::string p = path;
   std::vector<float> v; std::vector<uint32_t> t;
   int rc;
-  if (ends_with(p, ".ply") || ends_with(p, ".PLY")) rc = load_ply(p, v, t);
-  else if (ends_with(p, ".obj") || ends_with(p, ".OBJ")) rc = load_obj(p, v, t);
-  else { v.clear(); t.clear(); rc = SCN_OK; }                            // segmentator.cpp:130,141: neither branch -> empty mesh
+  try {                                                                  // nothing crosses the C boundary as an exception
+    if (ends_with(p, ".ply") || ends_with(p, ".PLY")) rc = load_ply(p, v, t);
+    else if (ends_with(p, ".obj") || ends_with(p, ".OBJ")) rc = load_obj(p, v, t);
+    else { v.clear(); t.clear(); rc = SCN_OK; }                          // segmentator.cpp:130,141: neither branch -> empty mesh
+  } catch (const std::bad_alloc&) { return scn::fail(SCN_ERR_FORMAT, "mesh file %s: out of memory while parsing", path);
+  } catch (const std::exception& e) { return scn::fail(SCN_ERR_FORMAT, "mesh file %s: %s", path, e.what()); }
   if (rc) return rc;
   *n_verts = v.size() / 3; *n_faces = t.size() / 3;
   *xyz = (float*)malloc(std::max<size_t>(1, v.size() * 4)); *tri = (uint32_t*)malloc(std::max<size_t>(1, t.size() * 4));

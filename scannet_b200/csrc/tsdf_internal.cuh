@@ -105,6 +105,7 @@ struct scn_tsdf {
   int alloc_group = 4;                           // frames of a batch walked by one k_alloc CTA (shared-memory key map reuse)
   int reserve_ctas = 0;                          // integrate CTAs per SM left free for the next batch's k_alloc (measured: 0 is best, SCN_TSDF_RESERVE)
   bool own_stream = false;
+  bool heap_zeroed = false;                      // the whole heap has been cleared once; later resets clear only the used prefix
   cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
   bool buf_used[2] = {false, false};
   int parity = 0;
