@@ -390,7 +390,6 @@ def main():
     ap.add_argument("--no-seg-c5", action="store_true", help="skip the 2M-vertex Segmentator case")
     ap.add_argument("--tma-kernel", action="store_true", help="force the cp.async.bulk staged integrate kernel (SCN_TSDF_KERNEL_TMA)")
     ap.add_argument("--column-kernel", action="store_true", help="force the register-resident column kernel (SCN_TSDF_KERNEL_COLUMN)")
-    ap.add_argument("--simple-kernel", action="store_true", help="use the plain 2-voxel/thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE)")
     ap.add_argument("--parity-frames", type=int, default=32, help="frames of the in-bench parity check against the oracle (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -432,7 +431,7 @@ def main():
 
     def make_volume(flags=0):
         p = tsdf.default_params(batch_frames=args.batch, max_blocks=1 << 20, hash_slots=1 << 22,
-                                flags=flags | (tsdf.KERNEL_SIMPLE if args.simple_kernel else 0) | (tsdf.KERNEL_TMA if args.tma_kernel else 0) |
+                                flags=flags | (tsdf.KERNEL_TMA if args.tma_kernel else 0) |
                                 (tsdf.KERNEL_COLUMN if args.column_kernel else 0))
         return tsdf.TsdfVolume(p, device=local, stream=torch.cuda.current_stream().cuda_stream)
 

@@ -179,7 +179,6 @@ typedef struct {
 } scn_tsdf_params;
 
 #define SCN_TSDF_NO_STATS   1u        /* skip the per-launch counters (N_u, N_b) */
-#define SCN_TSDF_KERNEL_SIMPLE 2u     /* first-generation integrate kernel (2 voxels/thread), kept for A/B profiles */
 #define SCN_TSDF_KERNEL_TMA    4u     /* always use the cp.async.bulk (TMA) staged integrate kernel (default: only for batches of <= 2 frames) */
 #define SCN_TSDF_KERNEL_COLUMN 8u     /* always use the register-resident column kernel */
 

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libscannet_b200.so")
+# SCN_B200_LIB: A/B runs of another build of the same library (bench scripts only)
+LIB_PATH = os.environ.get("SCN_B200_LIB") or os.path.join(_HERE, "lib", "libscannet_b200.so")
 
 
 class ScnError(RuntimeError):

@@ -15,7 +15,16 @@ constexpr int kDdaMaxSteps = 48;
 struct VolParams {
   float vs, trunc_base, trunc_scale, dmin, dmax, maxint, inv_range, ws15, inv_bs, depth_shift;
   int W, H, weight_max, const_w1;
+  // pixel rounding / gather addressing of the integrate kernels (tsdf.cu: frame_column)
+  float magic_x;             // 1.5*2^23 + jx: u + magic_x has round-half-even(u) + cx_raw in its raw bits
+  unsigned cx_raw;           // raw bits of magic_x
+  unsigned c_raw;            // (raw bits of 1.5*2^23) * W + cx_raw  (mod 2^32): raw gather index = pixel + c_raw, never wraps
+  unsigned sentinel_raw;     // raw index of the per-frame NaN element (pixel W*H)
+  unsigned Wm2, Hm2;         // W-2, H-2 (0 when the image is narrower than 3 pixels: the fast path is then never taken)
+  unsigned wmax8;            // 8 * weight_max (byte offset into the (w, 1/(w+1)) table)
+  int dm_stride;             // elements between consecutive frames of dm / rgbx: W*H + kDmPad
 };
+constexpr int kDmPad = 32;   // one NaN sentinel element per frame + padding to keep frames 128-byte aligned
 struct FrameParams {
   float T[12];       // cam2world rows 0..2
   float Rt[9];       // world->cam rotation
@@ -93,6 +102,7 @@ struct scn_tsdf {
   scn_tsdf_detail::Tables tb{};
   uint64_t cap = 0;
   float* dm = nullptr;
+  float* depth_lut = nullptr;       // raw u16 depth -> metres or NaN (spec step A + range test), 65536 entries
   unsigned* rgbx = nullptr;        // colour of the current batches repacked to one word per pixel (2 parities), allocated on first use
   uint16_t* d_depth[2] = {nullptr, nullptr};     // H2D staging, double buffered
   uint8_t* d_rgb[2] = {nullptr, nullptr};

@@ -13,7 +13,6 @@ from ._lib import TsdfParams, TsdfStats, check, lib
 
 VOXEL_DTYPE = np.dtype([("sdf", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("w", "u1")])
 NO_STATS = 1
-KERNEL_SIMPLE = 2
 KERNEL_TMA = 4
 KERNEL_COLUMN = 8
 

@@ -95,14 +95,6 @@ def test_full_resolution_frames(built):
     assert np.abs(g[1]["sdf"]).max() <= 0.02 + 0.01 * 6.0 + 1e-6
 
 
-def test_simple_kernel_variant(built):
-    """the plain 2-voxels-per-thread integrate kernel (SCN_TSDF_KERNEL_SIMPLE) gives the same bits"""
-    p = tsdf.default_params(width=160, height=120, max_blocks=1 << 15, hash_slots=1 << 17, batch_frames=5,
-                            flags=tsdf.KERNEL_SIMPLE)
-    D, C, P, K = synth.make_frames(6, seed=9, width=160, height=120, loop_frames=150, noise_mm=1.0)
-    assert_identical(*run_both(p, D, C, P, K))
-
-
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("batch,flag", [(1, 0), (2, 0), (5, tsdf.KERNEL_TMA), (3, tsdf.KERNEL_COLUMN)])
 def test_tma_staged_kernel_variant(built, batch, flag):
