@@ -280,6 +280,16 @@ def seg_bench(c5: bool):
         rec = {"verts": int(len(xyz)), "faces": int(len(tri)), "segments": int(len(set(seg.tolist()))), "bit_identical_to_cpu": bool((seg == ref).all()),
                "gpu_path_s": dt, "stages_ms": {k: round(v, 3) for k, v in zip(["h2d", "normals", "weights", "sort", "kruskal_host", "small_merge_host", "gather_d2h_labels", "total"], ms)},
                "sort_kernel_launches": launches, "cpu_port_s": t_port, "cpu_port_kind": "oracle/seg_oracle.c -O2, 1 thread, arrays in memory"}
+        # S5 on the device (SCN_SEG_DEVICE_UNIONFIND, csrc/seg.cu:k_kruskal_window) against the default host loop, same records
+        try:
+            segmentator.segment_mesh(xyz, tri, flags=segmentator.DEVICE_UNIONFIND)
+            t0 = time.perf_counter(); seg_d = segmentator.segment_mesh(xyz, tri, flags=segmentator.DEVICE_UNIONFIND); dt_d = time.perf_counter() - t0
+            ms_d, _ = segmentator.last_timings()
+            rec["unionfind_device_vs_host"] = {"kruskal_device_ms": round(ms_d[4], 3), "kruskal_host_ms": round(ms[4], 3), "device_rounds": segmentator.last_uf_rounds(),
+                                               "ids_identical": bool((seg_d == seg).all()), "gpu_path_s_with_device_unionfind": dt_d,
+                                               "default": "host loop" }
+        except Exception as e:
+            rec["unionfind_device_vs_host"] = {"error": repr(e)}
         ref_bin = os.path.join(ROOT, "oracle", "_ref", "segmentator_ref_O2")
         if os.path.exists(ref_bin):                  # the unmodified reference CLI in a child process (its stdout must not reach ours)
             with tempfile.TemporaryDirectory() as d:

@@ -61,7 +61,7 @@ int scn_mesh_load(const char* path, float** xyz, uint64_t* n_verts, uint32_t** t
 
 /* flags for scn_segment_mesh */
 #define SCN_SEG_DEFAULT        0
-#define SCN_SEG_HOST_UNIONFIND 1   /* run the Kruskal / small-segment replay on the host instead of the GPU kernel */
+#define SCN_SEG_DEVICE_UNIONFIND 1  /* run the Kruskal pass (S5) with the speculative-window device kernel instead of the host loop (default: host; see DESIGN.md §5 for the measured comparison) */
 /* test hook (scn_segment_graph only): override introsort's depth limit 2*floor(log2 n) to reach the heap-sort fallback */
 #define SCN_SEG_TEST_DEPTH(d)  (((d) & 0xFF) << 8)
 
@@ -93,6 +93,8 @@ int scn_segmentator_main(int argc, const char** argv);
 /* per-stage timings of the last scn_segment_* call on this thread, milliseconds:
  * [0] H2D, [1] normals, [2] weights, [3] sort, [4] kruskal, [5] small-merge, [6] labels+D2H, [7] total */
 int scn_segment_last_timings(float* ms8);
+/* rounds taken by the device union-find replay (SCN_SEG_DEVICE_UNIONFIND) in the last scn_segment_mesh call on this thread; 0 = host loop */
+uint64_t scn_segment_last_uf_rounds(void);
 
 /* ===================================================================== SensReader =====
  * Replaces: ml::SensorData                                  SensReader/c++/src/sensorData.h:285-1936

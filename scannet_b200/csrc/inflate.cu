@@ -3,15 +3,20 @@
 // depth never crosses PCIe and never touches a host core.
 //
 // A deflate stream has no internal synchronisation points, so the parallelism is across frames: ONE WARP PER FRAME.
-// All 32 lanes run the same bit reader and Huffman decoder redundantly (same addresses -> broadcast loads, no divergence,
-// no shuffles), lane 0 stores literals, and LZ77 matches are copied by the whole warp: byte i of a match is
-// out[o - dist + (i mod dist)], which only reads bytes that existed before the match, so the 32 lanes are independent
-// even when the match overlaps itself (runs of zeros: dist = 2, len = 258).  With hundreds of frames in flight every SM
-// sub-partition holds a few such warps; the 180 GB of HBM hold a whole scan decoded (5,578 frames = 3.4 GB).
-// Fixed-Huffman blocks (what stb's compressor — the one the ScanNet tools use — emits) are decoded arithmetically from a
-// bit-reversed 9-bit peek; dynamic blocks use canonical first-code/offset tables (16 compares at most) kept in shared
-// memory; stored blocks are copied.  The same source compiles for the host (lanes = 1) so the decoder is unit-tested
-// on the CPU against zlib streams of every block type.
+// What bounds a single stream is latency, not bandwidth: ~115-170 k symbols per 640x480 frame, ~60 % of them LZ77 matches
+// whose source bytes were written moments ago, at distances spread over the whole 32 KB window (measured on depth frames:
+// only ~45 % within 8 KB).  Read back from global memory every match costs an L2 round trip (the first version: 57 ms per
+// frame, ~950 cycles per symbol).  So each warp keeps the 32 KB deflate window as a ring in SHARED memory: literals and
+// matches are written to the ring and streamed to HBM (fire-and-forget stores), matches are copied ring -> ring by the
+// whole warp (byte i of a match is window[o - dist + (i mod dist)], which only reads bytes that existed before the match,
+// so the 32 lanes are independent even when the match overlaps itself), and the bit reader runs one 32-bit word ahead
+// of the decoder so that input loads are off the dependent chain.  All 32 lanes run the same bit reader and Huffman
+// decoder redundantly (same addresses -> broadcast loads, no divergence, no shuffles).  38.5 KB of shared memory per
+// stream = 5 streams per SM, 740 in flight.
+// Fixed-Huffman blocks (what stb's compressor - the one the ScanNet tools use - emits) and dynamic blocks go through the
+// same 9-bit lookahead tables (canonical first-code/offset tables beyond 9 bits) kept in shared memory; stored blocks are
+// copied.  The same source compiles for the host (one lane, no ring) so the decoder is unit-tested on the CPU against
+// zlib streams of every block type.
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -34,29 +39,40 @@ struct HuffTab {                     // canonical Huffman code, lengths 1..15
 enum { K_LIT = 0, K_BASE = 1, K_EOB = 2, K_BAD = 3 };
 enum { M_PLAIN = 0, M_LITLEN = 1, M_DIST = 2 };     // what the symbols of a table mean
 struct InflateScratch { HuffTab lit, dist; uint8_t lens[320]; };
+constexpr uint32_t kWin = 32768;                                   // deflate window = the shared-memory ring of the device decoder
+struct InflateScratchDev { uint8_t ring[kWin]; InflateScratch s; };
 
 // On the device the scratch lives in (dynamic) shared memory and is addressed directly; a generic pointer made the compiler
 // re-derive the shared window for every symbol.
 extern __shared__ __align__(16) unsigned char g_inflate_smem[];
 #ifdef __CUDA_ARCH__
-#define SCN_SCR(scr) (*reinterpret_cast<InflateScratch*>(g_inflate_smem))
+#define SCN_SCR(scr) (reinterpret_cast<InflateScratchDev*>(g_inflate_smem)->s)
+#define SCN_RING (reinterpret_cast<InflateScratchDev*>(g_inflate_smem)->ring)
 #else
 #define SCN_SCR(scr) (*(scr))
 #endif
 
-struct BitIn { const uint8_t* p; uint32_t n, pos; uint64_t bb; int bc; int over; };   // streams and frames are far below 4 GB: 32-bit offsets halve the address arithmetic
+struct BitIn { const uint8_t* p; uint32_t n, pos; uint64_t bb; int bc; int over; uint32_t ahead; int has_ahead; };   // streams and frames are far below 4 GB: 32-bit offsets halve the address arithmetic
 
 // Guarantees more than 32 valid bits (every decode step needs at most 32: a length code + extra bits is 20, a distance
 // code + extra bits 28, a stored-block header 32).  One aligned 32-bit load per four input bytes: the dependent chain of
 // a single warp is what bounds the kernel, so fewer, wider loads matter.  Past the end the buffer is zero-filled and the
 // shortfall remembered.
+// `ahead` holds the aligned word at b.pos, loaded one refill early: the load's latency overlaps the symbols decoded in
+// between (b.pos is advanced only when the word is consumed, so the stored-block path can still derive its source offset).
 SCN_HD void bi_refill(BitIn& b) {
   while (b.bc <= 32) {
-    if ((((size_t)(b.p + b.pos)) & 3) == 0 && b.pos + 4 <= b.n) { b.bb |= (uint64_t)(*(const uint32_t*)(b.p + b.pos)) << b.bc; b.pos += 4; b.bc += 32; }
+    if (b.has_ahead) {
+      b.bb |= (uint64_t)b.ahead << b.bc; b.pos += 4; b.bc += 32;
+      b.has_ahead = (b.pos + 4 <= b.n);
+      if (b.has_ahead) b.ahead = *(const uint32_t*)(b.p + b.pos);
+    }
+    else if ((((size_t)(b.p + b.pos)) & 3) == 0 && b.pos + 4 <= b.n) { b.has_ahead = 1; b.ahead = *(const uint32_t*)(b.p + b.pos); }
     else if (b.pos < b.n) { b.bb |= (uint64_t)b.p[b.pos++] << b.bc; b.bc += 8; }
     else { b.over += 8; b.bc += 8; }
   }
 }
+SCN_HD void bi_restart(BitIn& b, uint32_t pos) { b.pos = pos; b.bb = 0; b.bc = 0; b.over = 0; b.has_ahead = 0; }
 SCN_HD unsigned bi_peek(const BitIn& b, int n) { return (unsigned)(b.bb & ((1ull << n) - 1ull)); }
 SCN_HD void bi_drop(BitIn& b, int n) { b.bb >>= n; b.bc -= n; }
 SCN_HD unsigned bi_get(BitIn& b, int n) { const unsigned v = bi_peek(b, n); bi_drop(b, n); return v; }
@@ -178,9 +194,18 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
   const uint32_t n = (uint32_t)n_in, cap = (uint32_t)cap_in;
   const unsigned cmf = in[0], flg = in[1];
   if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return INF_BAD_HEADER;     // RFC 1950; preset dictionaries are not used
-  BitIn b{in, n, 2, 0ull, 0, 0};
+  BitIn b{in, n, 2, 0ull, 0, 0, 0u, 0};
   InflateScratch& S = SCN_SCR(scr);
   uint32_t o = 0;
+  // device: every output byte goes to the shared-memory ring (what later matches read) and to HBM; host: straight to `out`
+#ifdef __CUDA_ARCH__
+  uint8_t* const ring = SCN_RING;
+#define SCN_PUT(idx, v) do { const uint8_t v_ = (v); ring[(idx) & (kWin - 1u)] = v_; out[(idx)] = v_; } while (0)
+#define SCN_WIN(idx) ring[(idx) & (kWin - 1u)]
+#else
+#define SCN_PUT(idx, v) out[(idx)] = (v)
+#define SCN_WIN(idx) out[(idx)]
+#endif
   for (;;) {
     bi_refill(b);
     const unsigned last = bi_get(b, 1), type = bi_get(b, 2);
@@ -190,13 +215,14 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
       const unsigned len = bi_get(b, 16), nlen = bi_get(b, 16);
       if ((len ^ 0xFFFFu) != nlen || bi_overrun(b)) return INF_BAD_BLOCK;
       // the bytes still in the bit buffer come first, then straight from the input
-      const uint32_t src0 = b.pos - (uint32_t)((b.bc - b.over) / 8);
+      const uint32_t src0 = b.pos - (uint32_t)((b.bc - b.over) / 8);   // (a word held in `ahead` has not advanced b.pos)
       if (src0 + len > n) return INF_TRUNCATED;
       const uint32_t take = o + len > cap ? cap - o : len;
-      for (uint32_t i = (uint32_t)lane; i < take; i += LANES) out[o + i] = in[src0 + i];
+      lanes_sync<LANES>();
+      for (uint32_t i = (uint32_t)lane; i < take; i += LANES) SCN_PUT(o + i, in[src0 + i]);
       o += take;
       if (take < len) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
-      b.pos = src0 + len; b.bb = 0; b.bc = 0; b.over = 0;
+      bi_restart(b, src0 + len);
     } else if (type == 1 || type == 2) {
       if (type == 2) {
         bi_refill(b);
@@ -245,8 +271,8 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
         const uint32_t e = huff_decode(b, S.lit, M_LITLEN);
         const unsigned kind = (e >> 8) & 3u;
         if (kind == K_LIT) {
-          if (o >= cap) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
-          if (lane == 0) out[o] = (uint8_t)(e >> 16);
+          if (o >= cap) { lanes_sync<LANES>(); *produced = o; return bi_overrun(b) ? INF_TRUNCATED : INF_OUT_FULL; }   // (zero padding past a truncated stream decodes as literals)
+          if (lane == 0) SCN_PUT(o, (uint8_t)(e >> 16));
           ++o;
           continue;
         }
@@ -262,13 +288,10 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
         const bool full = o + len > cap;
         if (full) len = (unsigned)(cap - o);                      // the caller's frame is complete: write what fits and stop
         lanes_sync<LANES>();                                      // earlier literals / matches are visible to every lane
-        // (deferring the store of short matches so that the L2 round trip overlaps the next symbols' decoding was tried:
-        //  60.6 vs 57.2 ms per frame — the chain is bound by the decode itself, not by this load)
-        const uint8_t* src = out + (o - dist);
-        uint8_t* dst = out + o;
-        if (dist >= len) { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i]; }
-        else if ((dist & (dist - 1u)) == 0u) { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i & (dist - 1u)]; }
-        else { for (unsigned i = (unsigned)lane; i < len; i += LANES) dst[i] = src[i % dist]; }
+        const uint32_t so = o - dist;
+        if (dist >= len) { for (unsigned i = (unsigned)lane; i < len; i += LANES) SCN_PUT(o + i, SCN_WIN(so + i)); }
+        else if ((dist & (dist - 1u)) == 0u) { for (unsigned i = (unsigned)lane; i < len; i += LANES) SCN_PUT(o + i, SCN_WIN(so + (i & (dist - 1u)))); }
+        else { for (unsigned i = (unsigned)lane; i < len; i += LANES) SCN_PUT(o + i, SCN_WIN(so + i % dist)); }
         o += len;
         if (full) { lanes_sync<LANES>(); *produced = o; return INF_OUT_FULL; }
       }
@@ -279,6 +302,8 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
   lanes_sync<LANES>();
   *produced = o;
   return INF_OK;                                                  // the Adler-32 trailer is not checked (stb_image does not either)
+#undef SCN_PUT
+#undef SCN_WIN
 }
 
 // one warp per stream
@@ -385,7 +410,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   }
   std::vector<int> status(n); std::vector<unsigned long long> prod(n);
   if (e == cudaSuccess) {
-    k_inflate<<<n, 32, sizeof(InflateScratch), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    k_inflate<<<n, 32, sizeof(InflateScratchDev), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
     e = cudaMemcpyAsync(status.data(), g.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(prod.data(), g.d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st);

@@ -629,6 +629,114 @@ void host_small_merge(const Edge12* e, size_t nE, int min_verts, Forest& u) {
   }
 }
 
+// ---- S5 on the device: speculative-window replay of Kruskal-with-threshold (segmentator.cpp:71-91) -----------------------
+// One CTA keeps a window of up to 1024 pending edges in weight order (shared memory) and repeats rounds:
+//   1. every pending edge resolves the roots of its ends (read-only find with path compression; the forest lives in global
+//      memory, L2-resident) and registers itself on both components with atomicMin(owner[root], position);
+//   2. an edge whose ends share a root is a no-op for good (components only merge) and retires;
+//      a component whose EARLIEST pending edge is heavier than its threshold is frozen - a threshold only changes in a
+//      merge, a merge needs w <= threshold, and every pending or future edge is at least as heavy - so every edge touching
+//      it retires as rejected, in bulk;
+//      an edge that is the earliest pending edge of BOTH its components sees exactly the forest the sequential loop would
+//      show it, so it is decided now: it passed the two threshold tests above, so it joins (union by rank with the
+//      reference's argument order and tie rule, threshold = w + c / size);
+//      every other edge stays pending;
+//   3. the window is compacted in order and refilled from the sorted stream.
+// Merges decided in one round touch disjoint pairs of components, so they commute.  Identical forest (parents up to path
+// compression, ranks, sizes, thresholds, root identities) to the sequential loop; what limits it is the dependency chain of
+// merges into one growing component - one merge per component per round - see DESIGN.md §5 for the measured comparison
+// with the host loop, which stays the default.
+constexpr int kUfWindow = 1024;
+__device__ __forceinline__ int uf_find_dev(UfElt* U, int x) {
+  int y = x;
+  for (;;) { const int p = U[y].p; if (p == y) break; y = p; }
+  while (x != y) { const int n = U[x].p; if (n != y) U[x].p = y; x = n; }       // concurrent finds only ever write ancestors: benign
+  return y;
+}
+__global__ void __launch_bounds__(kUfWindow, 1)
+k_kruskal_window(const Edge12* __restrict__ e, unsigned nE, UfElt* U, int* owner, float c, unsigned long long* rounds_out) {
+  __shared__ Edge12 s_e[2][kUfWindow];
+  __shared__ unsigned s_warp[kUfWindow / 32];
+  __shared__ unsigned s_total;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  unsigned n_pend = 0, next = 0, cur = 0;
+  unsigned long long rounds = 0;
+  for (;;) {
+    const unsigned fill = min((unsigned)kUfWindow - n_pend, nE - next);
+    if ((unsigned)t < fill) s_e[cur][n_pend + t] = e[next + t];
+    n_pend += fill; next += fill;
+    if (n_pend == 0) break;
+    __syncthreads();
+    ++rounds;
+    Edge12 ed = {0.f, 0, 0};
+    int ra = 0, rb = 0; bool cand = false;
+    if ((unsigned)t < n_pend) {
+      ed = s_e[cur][t];
+      ra = uf_find_dev(U, ed.a); rb = uf_find_dev(U, ed.b);
+      cand = ra != rb;
+      if (cand) { atomicMin(&owner[ra], t); atomicMin(&owner[rb], t); }
+    }
+    __syncthreads();
+    bool keep = false, merge = false;
+    if (cand) {
+      const int fa = owner[ra], fb = owner[rb];
+      const float tha = U[ra].thr, thb = U[rb].thr;
+      if (s_e[cur][fa].w > tha || s_e[cur][fb].w > thb) { /* a frozen component: rejected for good */ }
+      else if (fa == t && fb == t) merge = true;
+      else keep = true;
+    }
+    __syncthreads();                                        // every read of the forest / owners precedes the writes below
+    if (cand) { owner[ra] = 0x7FFFFFFF; owner[rb] = 0x7FFFFFFF; }
+    if (merge) {                                            // universe::join(a, b) + the threshold update, segmentator.cpp:46-58,84-87
+      const int rka = U[ra].rank, rkb = U[rb].rank;
+      int root;
+      if (rka > rkb) { U[rb].p = ra; U[ra].size += U[rb].size; root = ra; }
+      else { U[ra].p = rb; U[rb].size += U[ra].size; if (rka == rkb) U[rb].rank = rkb + 1; root = rb; }
+      U[root].thr = __fadd_rn(ed.w, __fdiv_rn(c, (float)U[root].size));
+    }
+    // stable compaction of the edges that stay pending
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      unsigned v = s_warp[lane], inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned q = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += q; }
+      s_warp[lane] = inc - v;
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    if (keep) s_e[cur ^ 1][s_warp[warp] + __popc(bal & ((1u << lane) - 1u))] = ed;
+    n_pend = s_total;
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (t == 0 && rounds_out) *rounds_out = rounds;
+}
+__global__ void k_uf_init(UfElt* U, int* owner, size_t nV, float c) {
+  const size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  UfElt u; u.rank = 0; u.p = (int)v; u.size = 1; u.thr = c;
+  U[v] = u; owner[v] = 0x7FFFFFFF;
+}
+thread_local unsigned long long g_uf_rounds = 0;
+// Kruskal pass on the device over the pruned, sorted, still-resident records; the forest comes back to the host for the
+// small-segment pass and the labels (same structure as host_kruskal leaves).
+int device_kruskal(const Edge12* dE, size_t nK, size_t nV, float c, Forest& u, cudaStream_t st) {
+  u.resize(nV);
+  g_uf_rounds = 0;
+  if (!nV) return SCN_OK;
+  DevBuf dU, dOwner, dRounds;
+  if (dU.alloc(nV * sizeof(UfElt)) || dOwner.alloc(nV * 4) || dRounds.alloc(8)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc (device union-find)");
+  k_uf_init<<<(unsigned)((nV + 255) / 256), 256, 0, st>>>(dU.as<UfElt>(), dOwner.as<int>(), nV, c);
+  k_kruskal_window<<<1, kUfWindow, 0, st>>>(dE, (unsigned)nK, dU.as<UfElt>(), dOwner.as<int>(), c, dRounds.as<unsigned long long>());
+  CK(cudaMemcpyAsync(u.data(), dU.p, nV * sizeof(UfElt), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&g_uf_rounds, dRounds.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  return SCN_OK;
+}
+
 // Device: drop provable no-op records (see k_pair_first), copy the survivors to pinned host memory.  Returns the
 // pruned, still weight-sorted records in *out (pointer into a cached pinned buffer) and their count.
 int prune_and_download(const Rec* dRec, const unsigned* dTri, const Edge12* dSrc, size_t nE, cudaStream_t st, const Edge12** out, size_t* n_out,
@@ -717,7 +825,6 @@ struct Timer {
 int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF, float kthr, int32_t min_verts,
                  int32_t* seg_out, int flags, Edge12* edges_presort, Edge12* edges_sorted, float* normals_out,
                  int32_t* roots_after_kruskal) {
-  (void)flags;
   if ((!xyz && nV) || (!tri && nF) || !seg_out) return scn::fail(SCN_ERR_ARG, "null argument");
   if (nV > 0x7FFFFFFFull || 3 * nF > 0x7FFFFFFFull) return scn::fail(SCN_ERR_ARG, "mesh too large for 32-bit ids");
   for (int i = 0; i < 8; ++i) g_timings[i] = 0;
@@ -797,7 +904,8 @@ int segment_impl(const float* xyz, uint64_t nV, const uint32_t* tri, uint64_t nF
   if (rc) return rc;
   g_timings[6] = lapt.lap();
   Forest& u = g_forest;
-  host_kruskal(hE, nK, nV, kthr, u);
+  if (flags & SCN_SEG_DEVICE_UNIONFIND) { rc = device_kruskal(dE, nK, nV, kthr, u, st); if (rc) return rc; }
+  else host_kruskal(hE, nK, nV, kthr, u);
   g_timings[4] = lapt.lap();
   if (roots_after_kruskal) for (size_t q = 0; q < nV; ++q) { int y = (int)q; while (y != u[y].p) y = u[y].p; roots_after_kruskal[q] = y; }
   lapt.lap();
@@ -867,6 +975,11 @@ int scn_segment_last_timings(float* ms8) {
   if (!ms8) return scn::fail(SCN_ERR_ARG, "null argument");
   for (int i = 0; i < 8; ++i) ms8[i] = g_timings[i];
   return (int)g_sort_launches;
+}
+
+/* rounds taken by the device union-find replay of the last scn_segment_mesh call on this thread (0 = host loop was used) */
+uint64_t scn_segment_last_uf_rounds(void) {
+  return g_uf_rounds;
 }
 
 }  // extern "C"

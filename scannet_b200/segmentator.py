@@ -10,6 +10,7 @@ import numpy as np
 from ._lib import check, lib
 
 EDGE_DTYPE = np.dtype([("w", "<f4"), ("a", "<i4"), ("b", "<i4")])
+DEVICE_UNIONFIND = 1          # SCN_SEG_DEVICE_UNIONFIND: Kruskal pass on the GPU (speculative-window kernel) instead of the host loop
 
 
 def test_depth_flag(d: int) -> int:
@@ -55,3 +56,10 @@ def last_timings():
     ms = (C.c_float * 8)()
     n = check(lib().scn_segment_last_timings(ms))
     return list(ms), n
+
+
+def last_uf_rounds() -> int:
+    """rounds of the device union-find replay in the last segment_mesh call of this thread (0 = host loop)"""
+    f = lib().scn_segment_last_uf_rounds
+    f.restype = C.c_uint64
+    return int(f())

@@ -103,3 +103,18 @@ def test_corrupted_streams_never_escape_the_output_buffer(built):
         rc = L.scn_inflate_host(bytes(b), len(b), buf.ctypes.data, cap, C.byref(n))
         assert rc in (0, -4), rc                                            # SCN_OK or SCN_ERR_FORMAT
         assert n.value <= cap and (buf[cap:cap + 64] == 0xA5).all()
+
+
+def truncated_dynamic_stream():
+    """A dynamic-Huffman stream cut in the middle whose continuation by zero padding keeps decoding (the GPU path
+    accepted such frames while the host path rejected them).  Noise-free data whose all-zero code is a literal."""
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 4, 60000).astype(np.uint8).tobytes()            # 2-bit alphabet: short codes, zero bits decode to a literal
+    good = zlib.compress(raw, 6)
+    return raw, good[: len(good) // 3]
+
+
+def test_truncated_dynamic_block_is_an_error_on_the_host(built):
+    raw, bad = truncated_dynamic_stream()
+    with pytest.raises(ScnError, match="truncated"):
+        sens.inflate_host(bad, len(raw))

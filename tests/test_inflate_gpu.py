@@ -74,3 +74,12 @@ def test_device_errors(built):
     # a longer stream is cut at the frame size, like the host path
     sens.inflate_batch_device([zlib.compress(raw + b"tail" * 100)], len(raw), out.data_ptr())
     assert out[0].cpu().numpy().tobytes() == raw
+
+
+def test_truncated_dynamic_block_is_an_error_on_the_device_too(built):
+    """host and device must agree on a truncated stream (the device used to fill the frame from the zero padding)"""
+    from test_inflate_cpu import truncated_dynamic_stream
+    raw, bad = truncated_dynamic_stream()
+    out = torch.zeros((2, len(raw)), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ScnError, match="truncated"):
+        sens.inflate_batch_device([zlib.compress(raw, 6), bad], len(raw), out.data_ptr())

@@ -110,3 +110,16 @@ def test_unsupported_inputs_are_errors(tmp_path, built):
         mesh_load(q)
     with pytest.raises(ScnError):
         mesh_load(tmp_path / "missing.ply")
+
+
+def test_absurd_element_counts_are_errors_not_exceptions(tmp_path, built):
+    """ADVICE r01: `element vertex 999999999999999999` used to throw std::length_error through the C ABI (process abort)."""
+    import ctypes as C
+    from scannet_b200._lib import lib
+    for fmt, body in (("binary_little_endian", b"\x00" * 64), ("ascii", b"0 0 0\n")):
+        p = tmp_path / f"huge_{fmt}.ply"
+        p.write_bytes(("ply\nformat %s 1.0\nelement vertex 999999999999999999\nproperty float x\nproperty float y\nproperty float z\n"
+                       "element face 0\nproperty list uchar int vertex_indices\nend_header\n" % fmt).encode() + body)
+        px = C.POINTER(C.c_float)(); pt = C.POINTER(C.c_uint32)(); nv = C.c_uint64(); nf = C.c_uint64()
+        rc = lib().scn_mesh_load(str(p).encode(), C.byref(px), C.byref(nv), C.byref(pt), C.byref(nf))
+        assert rc != 0

@@ -147,3 +147,33 @@ def test_c5_two_million_vertices(built):
     assert (seg[seg] == seg).all()
     ref = ob.oracle_segment(xyz, tri)
     assert (seg == ref).all()
+
+
+@pytest.mark.parametrize("mesh", ["gates", "grid", "feature", "adversarial"])
+def test_device_unionfind_kernel_gives_the_same_ids(built, mesh):
+    """SCN_SEG_DEVICE_UNIONFIND: the speculative-window Kruskal kernel (csrc/seg.cu:k_kruskal_window) must leave exactly the
+    forest of the sequential loop (segmentator.cpp:71-91): same roots after the Kruskal pass, same final ids."""
+    import os
+    from scannet_b200 import segmentator, synth
+    if mesh == "gates":
+        import ctypes as C
+        from scannet_b200._lib import check, lib
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gates381.ply").encode()
+        px = C.POINTER(C.c_float)(); pt = C.POINTER(C.c_uint32)(); nv = C.c_uint64(); nf = C.c_uint64()
+        check(lib().scn_mesh_load(path, C.byref(px), C.byref(nv), C.byref(pt), C.byref(nf)))
+        xyz = np.ctypeslib.as_array(px, (nv.value * 3,)).copy().reshape(-1, 3); tri = np.ctypeslib.as_array(pt, (nf.value * 3,)).copy().reshape(-1, 3)
+        lib().scn_free(px); lib().scn_free(pt)
+    elif mesh == "grid":
+        xyz, tri = synth.make_grid_mesh(250, 200, seed=3)
+    elif mesh == "feature":
+        xyz, tri = synth.make_feature_mesh(300, 260, seed=4)
+    else:
+        xyz, tri = synth.make_adversarial_mesh(seed=1)
+    for kthr in (0.01, 0.0005):
+        h = segmentator.segment_mesh_debug(xyz, tri, kthr, 20)
+        d = segmentator.segment_mesh_debug(xyz, tri, kthr, 20, flags=segmentator.DEVICE_UNIONFIND)
+        assert segmentator.last_uf_rounds() > 0
+        assert (h["roots_after_kruskal"] == d["roots_after_kruskal"]).all()
+        assert (h["seg"] == d["seg"]).all()
+        ref = ob.oracle_segment(xyz, tri, kthr, 20)
+        assert (d["seg"] == ref).all()

@@ -376,3 +376,27 @@ def test_simd_and_scalar_idct_give_the_same_bytes(tmp_path, built):
     assert len(res["simd"]) == len(payloads)
     assert sum(isinstance(x, bytes) for x in res["simd"]) >= len(clean)
     assert res["simd"] == res["scalar"]
+
+
+def test_oversubscribed_jpeg_huffman_table_is_rejected_before_any_table_write(tmp_path, built):
+    """a DHT segment with counts[0]=200 used to index far outside the 512-entry fast table.  The decoder must
+    refuse it like stb_image does (bad code lengths), and a SOF whose size disagrees with the container must fail before any
+    plane is sized from the in-stream values."""
+    import cv2
+    from scannet_b200 import ScnError
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (16, 16, 3), dtype=np.uint8)
+    ok, buf = cv2.imencode(".jpg", img, [int(cv2.IMWRITE_JPEG_QUALITY), 80]); assert ok
+    good = bytes(buf)
+    i = good.index(b"\xff\xc4")                                           # first DHT segment
+    bad = bytearray(good); bad[i + 5] = 200                               # counts[0] = 200 codes of length 1
+    j = good.index(b"\xff\xc0")                                           # SOF0: claim a 65535 x 65535 image
+    huge = bytearray(good); huge[j + 5:j + 9] = b"\xff\xff\xff\xff"
+    D = np.full((1, 8, 8), 1000, np.uint16); P = np.eye(4, dtype=np.float32)[None]
+    for name, payload in (("dht", bad), ("sof", huge)):
+        p = str(tmp_path / f"{name}.sens")
+        synth.write_sens(p, D, np.zeros((1, 16, 16, 3), np.uint8), P, np.eye(4, dtype=np.float32), depth_comp=0, color_comp=2,
+                         jpeg_encoder=lambda x, _b=bytes(payload): _b)
+        s = SensFile(p)
+        with pytest.raises(ScnError):
+            s.color(0)
