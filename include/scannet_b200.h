@@ -126,6 +126,21 @@ int  scn_sens_frame_depth_u16(const scn_sens* s, uint64_t frame, uint16_t* out);
 int  scn_sens_frame_color_rgb8(const scn_sens* s, uint64_t frame, uint8_t* out);
 /* raw compressed payloads (pointers into the handle; valid until scn_sens_close) */
 int  scn_sens_frame_payload(const scn_sens* s, uint64_t frame, const uint8_t** color, const uint8_t** depth);
+
+/* ---- colour decode on the device (R4: sensorData.h:609-616 -> stb_image) ----------------------------------------------
+ * n baseline JPEG payloads (host pointers), every one width x height, decoded by the GPU (csrc/jpeg_gpu.cu), byte-identical
+ * to scn_sens_frame_color_rgb8 / the reference's stb_image path.
+ *   d_lut == NULL : d_out (device) receives n frames of width*height RGB8;
+ *   d_lut != NULL : device array of out_px ints = colour pixel index per output pixel (-1 = none -> black); d_out receives n
+ *                   frames of out_px RGB8 (colour registered to the depth image, what scn_tsdf_integrate_device consumes).
+ * Streams the device path does not handle (progressive, multi-scan, exotic sampling) or flags as corrupt go through the host
+ * decoder and are uploaded: same bytes, same errors.  *n_on_device (optional) = frames decoded by the GPU.  `stream` =
+ * cudaStream_t (0 = default); returns after the work has completed. */
+int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_bytes, uint32_t n, uint32_t width, uint32_t height,
+                                 const int32_t* d_lut, uint32_t out_px, void* d_out, void* stream, uint32_t* n_on_device);
+/* colour frames [first, first+n) of an open stream into device memory (JPEG on the GPU; raw / PNG via the host decoder) */
+int scn_sens_decode_color_device(const scn_sens* s, uint64_t first, uint32_t n, const int32_t* d_lut, uint32_t out_px, void* d_out,
+                                 void* stream, uint32_t* n_on_device);
 /* Read-ahead decoder: the counterpart of SensorData::RGBDFrameCacheRead (sensorData.h:1717-1835), which the reconstruction
  * binaries pull frames from.  Background threads (the reference has one; n_threads <= 0 picks min(8, cores)) decode depth and
  * colour of up to cache_size frames ahead of the consumer, in stream order.  scn_sens_cache_next copies the next frame into the

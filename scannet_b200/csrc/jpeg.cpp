@@ -21,61 +21,14 @@
 #include <cstring>
 #include <vector>
 
+#include "jpeg_tables.h"
 #include "scn_common.h"
 
 namespace {
 
-const uint8_t kZig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11,4,5,12,19,26,33,40,48,41,34,27,20,13,6,7,14,21,28,35,42,49,56,57,50,43,36,
-                               29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63,
-                               63,63,63,63,63,63,63,63,63,63,63,63,63,63,63};
-
-constexpr int kFastBits = 9;
-struct HuffTab {
-  bool present = false;
-  int maxcode[18]; int valptr[17]; int mincode[17]; uint8_t vals[256];
-  uint16_t fast[1 << kFastBits];          // (symbol << 4) | length for codes of <= 9 bits, 0xFFFF = longer code
-  int16_t fast_ac[1 << kFastBits];        // AC tables: (value << 8) | (run << 4) | (code+magnitude bits) when both fit in 9 bits, else 0
-  void build_fast_ac() {
-    for (int i = 0; i < (1 << kFastBits); ++i) {
-      fast_ac[i] = 0;
-      const uint16_t e = fast[i];
-      if (e == 0xFFFF) continue;
-      const int rs = e >> 4, len = e & 15, run = rs >> 4, mag = rs & 15;
-      if (mag && len + mag <= kFastBits) {
-        int k = ((i << len) & ((1 << kFastBits) - 1)) >> (kFastBits - mag);
-        if (k < (1 << (mag - 1))) k -= (1 << mag) - 1;                       // extend
-        if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)((k * 256) + (run * 16) + (len + mag));
-      }
-    }
-  }
-  bool build(const uint8_t* counts, const uint8_t* symbols, int nsym) {
-    int code = 0, k = 0;
-    // validate before any table write (stb_image.h:1590-1615 rejects over-subscribed lengths before building its fast
-    // table): an over-subscribed code would index far outside fast[]
-    for (int l = 1, c = 0, tot = 0; l <= 16; ++l) {
-      c += counts[l - 1]; tot += counts[l - 1];
-      if (c > (1 << l) || tot > nsym || tot > 256) return false;
-      c <<= 1;
-    }
-    for (int i = 0; i < (1 << kFastBits); ++i) fast[i] = 0xFFFF;
-    for (int l = 1; l <= 16; ++l) {
-      valptr[l] = k; mincode[l] = code;
-      if (l <= kFastBits)
-        for (int j = 0; j < counts[l - 1]; ++j) {
-          const int c = (code + j) << (kFastBits - l);
-          for (int f = 0; f < (1 << (kFastBits - l)); ++f) fast[c + f] = (uint16_t)((symbols[k + j] << 4) | l);
-        }
-      code += counts[l - 1]; k += counts[l - 1];
-      if (code > (1 << l)) return false;
-      maxcode[l] = counts[l - 1] ? code - 1 : -1;
-      code <<= 1;
-    }
-    maxcode[17] = 0x7FFFFFFF;
-    memcpy(vals, symbols, (size_t)nsym);
-    present = true;
-    return true;
-  }
-};
+using scn_jpeg::HuffTab;
+using scn_jpeg::kFastBits;
+const uint8_t* const kZig = scn_jpeg::kZigHost;
 
 struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0, x = 0, y = 0, w2 = 0, h2 = 0, coeff_w = 0; std::vector<uint8_t> data; std::vector<short> coeff; };
 
@@ -351,6 +304,7 @@ int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_
   if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return fail(SCN_ERR_FORMAT, "not a JPEG (no SOI)");
   uint8_t quant[4][64]; bool have_q[4] = {false, false, false, false};
   HuffTab hdc[4], hac[4];
+  for (int i = 0; i < 4; ++i) hdc[i].present = hac[i].present = 0;
   Comp comp[3];
   // plane buffers are leased from the calling thread and handed back on every exit path: a decoder pool of 64 threads doing
   // a 460 KB allocation + page faults per frame serialised on the process's memory map (31 ms per 128-frame chunk instead of 7)

@@ -71,6 +71,15 @@ class SensFile:
         """Frames [first, first+n) inflated on the GPU straight into device memory at `d_out_ptr` (n*H*W uint16)."""
         check(_L().scn_sens_decode_depth_device(self._h, C.c_uint64(first), C.c_uint32(n), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
+    def decode_color_device(self, first: int, n: int, d_out_ptr: int, d_lut_ptr: int = 0, out_px: int = 0, stream: int = 0) -> int:
+        """Colour frames [first, first+n) decoded on the GPU into device memory at `d_out_ptr` (RGB8; whole frames, or `out_px`
+        pixels per frame picked through the device int32 map `d_lut_ptr`).  Returns the number of frames the device decoded
+        (the rest went through the host decoder)."""
+        k = C.c_uint32()
+        check(_L().scn_sens_decode_color_device(self._h, C.c_uint64(first), C.c_uint32(n), C.c_void_p(d_lut_ptr) if d_lut_ptr else None,
+                                                C.c_uint32(out_px), C.c_void_p(d_out_ptr), C.c_void_p(stream), C.byref(k)))
+        return k.value
+
     def read_ahead(self, cache_size: int = 16, n_threads: int = 0):
         """Iterator over (depth uint16 [H,W], colour uint8 [H,W,3], ts_depth, ts_color) decoded by background threads, in stream
         order — the RGBDFrameCacheRead pattern (sensorData.h:1717-1835)."""
@@ -127,6 +136,18 @@ def inflate_batch_device(streams, frame_bytes: int, d_out_ptr: int, stream: int 
     ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
     lens = (C.c_uint64 * max(n, 1))(*[len(b) for b in streams])
     check(_L().scn_inflate_batch_device(ptrs, lens, C.c_uint32(n), C.c_uint64(frame_bytes), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+
+def jpeg_decode_batch_device(jpegs, width: int, height: int, d_out_ptr: int, d_lut_ptr: int = 0, out_px: int = 0, stream: int = 0) -> int:
+    """JPEG payloads (bytes objects) -> RGB8 frames at device pointer `d_out_ptr`; returns how many the GPU decoded itself."""
+    n = len(jpegs)
+    bufs = [np.frombuffer(b, np.uint8) if len(b) else np.zeros(1, np.uint8) for b in jpegs]
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+    lens = (C.c_uint64 * max(n, 1))(*[len(b) for b in jpegs])
+    k = C.c_uint32()
+    check(_L().scn_jpeg_decode_batch_device(ptrs, lens, C.c_uint32(n), C.c_uint32(width), C.c_uint32(height), C.c_void_p(d_lut_ptr) if d_lut_ptr else None,
+                                            C.c_uint32(out_px), C.c_void_p(d_out_ptr), C.c_void_p(stream), C.byref(k)))
+    return k.value
 
 
 def inflate_host(data: bytes, cap: int) -> bytes:
