@@ -5,8 +5,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
 nproc >> $OUT/gpu_$TAG.txt; lscpu | grep -E "Model name|Socket|NUMA|Thread" >> $OUT/gpu_$TAG.txt; free -g >> $OUT/gpu_$TAG.txt
-timeout 900 python -m pytest tests/test_tsdf_gpu.py tests/test_tsdf_bench_config_gpu.py tests/test_pipeline_gpu.py tests/test_filter_gpu.py -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_tsdf_$TAG.log
-cat $OUT/pytest_tsdf_$TAG.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > $OUT/pytest_gpu_$TAG.log
+cat $OUT/pytest_gpu_$TAG.log
 ( time timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --no-seg > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err ) 2>&1 | tail -3; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
 if [ -f build/ab/r01/libscannet_b200.so ]; then
   SCN_B200_LIB=$PWD/build/ab/r01/libscannet_b200.so timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --no-seg > $OUT/bench_r01kernels_$TAG.json 2> $OUT/bench_r01kernels_$TAG.err; cat $OUT/bench_r01kernels_$TAG.json; tail -3 $OUT/bench_r01kernels_$TAG.err
@@ -21,6 +21,5 @@ if [ "${NCU:-1}" = "1" ]; then
       python bench.py --steps 2 --warmup 1 --scene-frames 96 --frames-per-step 96 --no-cpu --no-seg --parity-frames 0 > $OUT/ncu_full_alloc_$TAG.log 2>&1
   tail -3 $OUT/ncu_full_$TAG.log
 fi
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_gpu_$TAG.log
-cat $OUT/pytest_gpu_$TAG.log
+( time timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/bench_full_$TAG.json 2> $OUT/bench_full_$TAG.err ) 2>&1 | tail -3; cat $OUT/bench_full_$TAG.json; tail -5 $OUT/bench_full_$TAG.err
 ( time timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err ) 2>&1 | tail -3; tail -c 1500 $OUT/bench_ref_$TAG.json
