@@ -70,7 +70,7 @@ def render_depth_torch(sc, P, device, chunk=50):
     Returns uint16 depth [N,H,W] (mm).  Data generation only — not part of any timed region."""
     import torch
     N = len(P)
-    out = torch.empty((N, H, W), dtype=torch.int16, device=device)
+    out = torch.empty((N, sc.H, sc.W), dtype=torch.int16, device=device)
     rays = torch.as_tensor(sc.rays_cam, dtype=torch.float64, device=device)          # [H,W,3]
     size = torch.as_tensor(sc.size, dtype=torch.float64, device=device)
     for s in range(0, N, chunk):
@@ -374,6 +374,84 @@ def sens_bench(n_frames=120):
     return out
 
 
+# ----------------------------------------------------------------------------- decode-inclusive pipeline (configs[2])
+def make_sens_file(path, n_frames, seed, device, color_wh=(1296, 968), with_color=True, threads=None, chunk=128):
+    """A synthetic scan as a .sens file: 640x480 zlib depth (+ 1296x968 JPEG colour, ScannerApp/README.md:20-23) of the box-room
+    scene along one camera loop.  Rendered on the device with torch, compressed by a host thread pool (zlib level 6, JPEG q85 —
+    both release the GIL).  Returns (bytes written, seconds)."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    import cv2
+    import torch
+    from scannet_b200 import synth
+    t0 = time.perf_counter()
+    threads = threads or min(64, os.cpu_count() or 1)
+    sc, P = scene_poses(n_frames, seed, n_frames)
+    CW, CH = color_wh
+    scc = synth.BoxRoomScene(size=(6.0, 5.0, 3.0), seed=seed, width=CW, height=CH, fx=synth.FX * CW / W, fy=synth.FY * CH / H,
+                             cx=(synth.CX + 0.5) * CW / W - 0.5, cy=(synth.CY + 0.5) * CH / H - 0.5)
+    Kc = scc.intrinsics()
+
+    def enc(args):
+        d, c = args
+        ok, buf = (True, None) if c is None else cv2.imencode(".jpg", c, [int(cv2.IMWRITE_JPEG_QUALITY), 85])
+        return (b"" if c is None else buf.tobytes()), zlib.compress(d.tobytes(), 6)
+
+    with synth.SensWriter(path, n_frames, (W, H), (CW, CH) if with_color else (1, 1), sc.intrinsics(), Kc if with_color else None,
+                          color_comp=2 if with_color else 0) as wr, ThreadPoolExecutor(threads) as ex:
+        for s0 in range(0, n_frames, chunk):
+            Pc = P[s0:s0 + chunk]
+            d = render_depth_torch(sc, Pc, device).cpu().numpy().view(np.uint16)
+            if with_color:
+                dc = render_depth_torch(scc, Pc, device).to(torch.float32)                   # smooth shading of the same geometry at colour resolution
+                col = torch.stack((128 + 100 * torch.sin(dc * 0.004), 128 + 100 * torch.sin(dc * 0.0023 + 1.0), 128 + 100 * torch.cos(dc * 0.0011)), -1)
+                col = col.clamp(0, 255).to(torch.uint8).cpu().numpy()
+                items = [(d[i], col[i]) for i in range(len(Pc))]
+            else:
+                items = [(d[i], None) for i in range(len(Pc))]
+            for i, (cb, db) in enumerate(ex.map(enc, items)):
+                wr.add(cb if with_color else bytes(3), db, Pc[i])
+    return os.path.getsize(path), time.perf_counter() - t0
+
+
+def pipeline_bench(args, device):
+    """BASELINE.json configs[2] stand-in: a 5,578-frame scan (1296x968 JPEG colour + 640x480 zlib depth) through the product
+    driver scn_fuse_scene: compressed payloads -> GPU inflate + GPU JPEG -> hashed 4 mm TSDF -> marching cubes -> PLY."""
+    import tempfile
+    from scannet_b200 import fuse as sfuse
+    out = {}
+    with tempfile.TemporaryDirectory(dir=os.environ.get("SCN_BENCH_TMP")) as d:
+        p = os.path.join(d, "scene.sens")
+        nbytes, gen_s = make_sens_file(p, args.c3_frames, 7, device)
+        out["input"] = {"frames": args.c3_frames, "depth": "640x480 u16 zlib-6", "colour": "1296x968 JPEG q85 4:2:0", "file_gb": round(nbytes / 1e9, 3),
+                        "generation_s": round(gen_s, 1), "note": "synthetic stand-in for scene0000_00 (licence-gated, SURVEY.md §8d)"}
+        for mode in ("gpu", "host"):
+            rep = sfuse.fuse_scene(p, os.path.join(d, f"mesh_{mode}.ply"), max_blocks=1 << 22, hash_slots=1 << 24, decode_mode=mode)
+            out[mode + "_decode"] = rep
+        out["meshes_identical"] = open(os.path.join(d, "mesh_gpu.ply"), "rb").read() == open(os.path.join(d, "mesh_host.ply"), "rb").read()
+    return out
+
+
+def file_to_tsdf(args, device, rank, world, grp):
+    """configs[1]/[3] decode-inclusive: every rank fuses its own 1000-frame .sens (depth zlib + 640x480 JPEG colour off) from file
+    through scn_fuse_scene; the job's rate = all frames / max over ranks of the wall time (barrier before the start)."""
+    import tempfile
+    from scannet_b200 import fuse as sfuse
+    with tempfile.TemporaryDirectory(dir=os.environ.get("SCN_BENCH_TMP")) as d:
+        p = os.path.join(d, f"scene{rank}.sens")
+        make_sens_file(p, args.scene_frames, 100 + rank, device, with_color=False, threads=max(4, (os.cpu_count() or 8) // max(world, 1)))
+        sfuse.fuse_scene(p, None, decode_mode="gpu", device=device.index or 0)                 # warm-up: context, staging buffers, module load
+        grp.barrier()
+        t0 = time.perf_counter()
+        rep = sfuse.fuse_scene(p, None, decode_mode="gpu", device=device.index or 0)
+        dt = time.perf_counter() - t0
+        frames, ms = grp.reduce_throughput(rep["frames_integrated"], dt * 1e3)
+        res = {"value": frames / (ms / 1e3), "unit": UNIT, "frames": frames, "wall_s_max_over_ranks": ms / 1e3,
+               "what": "file (.sens, zlib depth) -> GPU inflate -> TSDF, one scene per GPU, no mesh; includes opening + parsing the file",
+               "rank0": rep}
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def load_traffic():
     try:
@@ -400,6 +478,7 @@ def main():
     ap.add_argument("--no-seg-c5", action="store_true", help="skip the 2M-vertex Segmentator case")
     ap.add_argument("--tma-kernel", action="store_true", help="force the cp.async.bulk staged integrate kernel (SCN_TSDF_KERNEL_TMA)")
     ap.add_argument("--column-kernel", action="store_true", help="force the register-resident column kernel (SCN_TSDF_KERNEL_COLUMN)")
+    ap.add_argument("--c3-frames", type=int, default=5578, help="frames of the configs[2] stand-in scan in the pipeline side section (0 = skip)")
     ap.add_argument("--parity-frames", type=int, default=32, help="frames of the in-bench parity check against the oracle (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -501,6 +580,13 @@ def main():
     vol2.sync()
     vol2.close()
     clocks = sampler.stop() if sampler else None
+    # ---- decode-inclusive: .sens file -> TSDF through the product driver, one scene per rank ------------------------------
+    f2t = None
+    if not args.no_seg:
+        try:
+            f2t = file_to_tsdf(args, dev, rank, world, grp)
+        except Exception as e:
+            f2t = {"error": repr(e)}
 
     # ---- in-bench parity check: the first frames of scene 0 through the same entry point, bit for bit against the oracle ----
     parity = None
@@ -565,6 +651,7 @@ def main():
                                  "the ncu capture) ~10x lower than that figure, so frac can exceed 1: the kernel is bound by instruction issue "
                                  "(issue_active), not by HBM; the two kernels of consecutive batches overlap, so their times sum to more than the step"},
             "parity_check": parity,
+            "file_to_tsdf": f2t,
             "clocks": clocks,
         }
         if world == 1 and not args.no_seg:          # side sections first: the CPU arm below perturbs host-side timings measured after it
@@ -576,6 +663,11 @@ def main():
                 line["sens"] = sens_bench()
             except Exception as e:
                 line["sens"] = {"error": repr(e)}
+            if args.c3_frames > 0:
+                try:
+                    line["pipeline_c3"] = pipeline_bench(args, dev)
+                except Exception as e:
+                    line["pipeline_c3"] = {"error": repr(e)}
         if not args.no_cpu and world == 1:          # CPU baseline: rank 0 at N=1 only
             line["cpu_baseline"], _ = cpu_arm(args, steps=1, warmup=0)
         emit(line)

@@ -42,6 +42,8 @@ void  scn_free(void* p);                      /* frees buffers this library mall
  * scn_tsdf_integrate_device); the copies return when the transfer has completed */
 void* scn_device_alloc(size_t bytes);
 void  scn_device_free(void* p);
+int   scn_set_device(int device);                     /* cudaSetDevice for the calling thread (multi-GPU drivers) */
+int   scn_device_mem_info(size_t* used_bytes, size_t* total_bytes);
 int   scn_stream_create(void** stream_out);          /* non-blocking cudaStream_t */
 void  scn_stream_destroy(void* stream);
 int   scn_memcpy_h2d(void* d_dst, const void* src, size_t bytes, void* stream);
@@ -298,7 +300,33 @@ int  scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byt
 /* host build of the same decoder source (one lane): used by the CPU test-suite; not a product path */
 int  scn_inflate_host(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* produced);
 
-/* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract. */
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scene fusion driver: .sens -> hashed TSDF -> (optionally) marching cubes -> <out>.ply — the contract of the reference's
+ * external reconstruction stage (Server/scan_processor.py:27-35,123-138), one scene per GPU (Server/process.py:75 runs one
+ * scan per GPU at a time).  decode_mode: NULL = automatic, "gpu" = compressed payloads decoded in HBM,
+ * "host" = host thread pool.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct scn_fuse_report {
+  int32_t  status;                 /* 0 or the error code of this scene (scn_fuse_many) */
+  int32_t  device;
+  int32_t  gpu_decode;             /* 1 = payloads were decoded on the GPU */
+  uint32_t color_frames_on_device; /* JPEG frames the device decoder handled itself (the rest went through the host decoder) */
+  uint64_t frames_integrated, frames_skipped, frames_skipped_pose;
+  uint64_t blocks_allocated, voxels_updated;
+  uint64_t mesh_vertices, mesh_faces;
+  uint64_t device_bytes_in_use;    /* cudaMemGetInfo after fusion: volume + decode staging */
+  double   fuse_s;                 /* first frame in -> last frame integrated, decode included */
+  double   decode_wait_s;          /* of which the integrator waited for the decoders */
+  double   depth_decode_s, color_decode_s;   /* busy time of the two decoder threads (overlaps fuse_s) */
+  double   mc_s, ply_s, total_s;   /* marching cubes, PLY write, everything incl. opening the file */
+} scn_fuse_report_t;
+int  scn_fuse_scene(const char* sens_path, const char* out_ply /* NULL: no mesh */, const scn_tsdf_params* params, int device,
+                    const char* decode_mode, scn_fuse_report_t* report);
+/* n_scenes scenes over n_devices GPUs, one scene per GPU at a time, no data-path collective; reports[i] per scene */
+int  scn_fuse_many(const char* const* sens_paths, const char* const* out_plys /* NULL or per-scene NULL: no mesh */, uint32_t n_scenes,
+                   const scn_tsdf_params* params, const int* devices, uint32_t n_devices, const char* decode_mode,
+                   scn_fuse_report_t* reports);
+/* `fuse <params.txt> <file.sens> [out.ply]` — the recons/improve stage contract; `fuse --gpus N <params.txt> a.sens b.sens ...` */
 int  scn_fuse_main(int argc, const char** argv);
 
 #ifdef __cplusplus

@@ -54,6 +54,14 @@ void* scn_device_alloc(size_t bytes) {
   return p;
 }
 void scn_device_free(void* p) { if (p) cudaFree(p); }
+int scn_set_device(int device) { SCN_CUDA_TRY(cudaSetDevice(device)); return SCN_OK; }
+int scn_device_mem_info(size_t* used_bytes, size_t* total_bytes) {
+  size_t fr = 0, tot = 0;
+  SCN_CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+  if (used_bytes) *used_bytes = tot - fr;
+  if (total_bytes) *total_bytes = tot;
+  return SCN_OK;
+}
 int scn_stream_create(void** out) {
   if (!out) return scn::fail(SCN_ERR_ARG, "null argument");
   cudaStream_t s = nullptr;

@@ -302,3 +302,43 @@ def write_sens(path, depth: np.ndarray, rgb: np.ndarray | None, poses: np.ndarra
             f.write(struct.pack("<QQQQ", i * 33333, i * 33333, len(cb), len(db)))
             f.write(cb); f.write(db)
         f.write(struct.pack("<Q", 0))
+
+
+class SensWriter:
+    """Streaming .sens v4 writer for pre-compressed payloads (same layout as write_sens): the frame count goes into the header up
+    front, frames are appended one by one, so a several-GB synthetic scan never sits in memory."""
+
+    def __init__(self, path, n_frames: int, depth_wh, color_wh, K_depth, K_color=None, depth_shift: float = 1000.0,
+                 depth_comp: int = 1, color_comp: int = 2, sensor_name: str = "synthetic"):
+        self.f = open(path, "wb"); self.n = n_frames; self.i = 0
+        f = self.f
+        f.write(struct.pack("<I", 4))
+        nm = sensor_name.encode("ascii")
+        f.write(struct.pack("<Q", len(nm))); f.write(nm)
+        eye = np.eye(4, dtype=np.float32)
+        for m in (K_depth if K_color is None else K_color, eye, K_depth, eye):
+            f.write(np.asarray(m, "<f4").tobytes())
+        f.write(struct.pack("<ii", color_comp, depth_comp))
+        f.write(struct.pack("<IIII", color_wh[0], color_wh[1], depth_wh[0], depth_wh[1]))
+        f.write(struct.pack("<f", depth_shift))
+        f.write(struct.pack("<Q", n_frames))
+
+    def add(self, color_payload: bytes, depth_payload: bytes, pose):
+        f = self.f
+        f.write(np.asarray(pose, "<f4").tobytes())
+        f.write(struct.pack("<QQQQ", self.i * 33333, self.i * 33333, len(color_payload), len(depth_payload)))
+        f.write(color_payload); f.write(depth_payload)
+        self.i += 1
+
+    def close(self):
+        assert self.i == self.n, (self.i, self.n)
+        self.f.write(struct.pack("<Q", 0)); self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        if a[0] is None:
+            self.close()
+        else:
+            self.f.close()

@@ -114,3 +114,58 @@ def test_fuse_gpu_decode_writes_the_same_mesh(built, tmp_path):
         assert ("GPU inflate" in r.stdout) == (mode == "gpu")
         out[mode] = (d / "scene_vh.ply").read_bytes()
     assert out["host"] == out["gpu"]
+
+
+def _jpeg_encoder(q=85):
+    import cv2
+    def enc(rgb):
+        ok, buf = cv2.imencode(".jpg", rgb[:, :, ::-1], [int(cv2.IMWRITE_JPEG_QUALITY), q, int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR), 0x221111])
+        assert ok
+        return buf.tobytes()
+    return enc
+
+
+def test_fuse_jpeg_colour_decoded_on_the_gpu_gives_the_host_decoders_mesh(built, tmp_path):
+    """.sens with zlib depth + JPEG colour at a different resolution than depth: `fuse` with everything decoded in HBM (GPU
+    inflate + GPU JPEG sampling only the registered pixels) writes the same coloured PLY as the host thread pool."""
+    D, Cc, P, K = synth.make_frames(36, seed=7, width=160, height=120, loop_frames=500, invalid_pose_every=9, noise_mm=1.0)
+    big = np.repeat(np.repeat(Cc, 2, axis=1), 2, axis=2)[:, :236, :318]                      # 318x236 colour for 160x120 depth
+    Kc = K.copy(); Kc[0, 0] *= 318 / 160; Kc[1, 1] *= 236 / 120; Kc[0, 2] = (K[0, 2] + 0.5) * 318 / 160 - 0.5; Kc[1, 2] = (K[1, 2] + 0.5) * 236 / 120 - 0.5
+    params = tmp_path / "params.txt"
+    params.write_text("s_SDFVoxelSize = 0.008f;\ns_SDFTruncation = 0.04f;\ns_SDFTruncationScale = 0.01f;\ns_hashNumSDFBlocks = 60000;\n")
+    out = {}
+    for mode in ("host", "gpu"):
+        d = tmp_path / mode; d.mkdir()
+        synth.write_sens(str(d / "scene.sens"), D, big, P, K, K_color=Kc, depth_comp=1, color_comp=2, jpeg_encoder=_jpeg_encoder())
+        r = subprocess.run([os.path.join(BIN, "fuse"), str(params), str(d / "scene.sens")], capture_output=True, text=True,
+                           env=dict(os.environ, SCN_FUSE_DECODE=mode, SCN_FUSE_CHUNK="16"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert ("GPU JPEG" in r.stdout) == (mode == "gpu")
+        assert "integrated 32 frames (4 skipped" in r.stdout
+        out[mode] = (d / "scene_vh.ply").read_bytes()
+    assert out["host"] == out["gpu"]
+    assert b"property uchar red" in out["gpu"][:400]
+
+
+def test_fuse_many_scenes_library_driver(built, tmp_path):
+    """scn_fuse_many: several scenes over the visible GPUs (one scene per GPU at a time); every report filled, meshes identical to
+    the single-scene driver's"""
+    from scannet_b200 import fuse as sfuse
+    paths = []
+    for i in range(3):
+        D, Cc, P, K = synth.make_frames(20 + 4 * i, seed=20 + i, width=160, height=120, loop_frames=400)
+        p = tmp_path / f"s{i}.sens"
+        synth.write_sens(str(p), D, None, P, K, depth_comp=1, color_comp=0)
+        paths.append(str(p))
+    over = dict(voxel_size=0.008, trunc_base=0.04, max_blocks=60000, hash_slots=1 << 18)
+    outs = [str(tmp_path / f"m{i}.ply") for i in range(3)]
+    import torch
+    devs = list(range(min(2, torch.cuda.device_count())))
+    reps = sfuse.fuse_many(paths, outs, devices=devs, **over)
+    assert [r["frames_integrated"] for r in reps] == [20, 24, 28] and all(r["status"] == 0 and r["mesh_faces"] > 1000 for r in reps)
+    single = sfuse.fuse_scene(paths[1], str(tmp_path / "single.ply"), **over)
+    assert single["mesh_vertices"] == reps[1]["mesh_vertices"]
+    assert (tmp_path / "single.ply").read_bytes() == (tmp_path / "m1.ply").read_bytes()
+    from scannet_b200 import ScnError
+    with pytest.raises(ScnError):
+        sfuse.fuse_many(paths + [str(tmp_path / "missing.sens")], None, devices=devs, **over)
