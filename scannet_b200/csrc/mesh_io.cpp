@@ -405,22 +405,15 @@ int scn_segs_load(const char* path, uint32_t** seg_out, uint64_t* n_out, float* 
   return SCN_OK;
 }
 
-int scn_segmentator_main(int argc, const char** argv) {
-  if (argc < 2) {
-    printf("Usage: ./segmentator input.ply [kThresh] [segMinVerts] (defaults: kThresh=0.01 segMinVerts=20)\n");
-    return 255;                                                          // exit(-1)
-  }
-  const std::string plyFile = argv[1];
-  const float kthr = argc > 2 ? (float)atof(argv[2]) : 0.01f;
-  const int segMinVerts = argc > 3 ? atoi(argv[3]) : 20;
+// one mesh: segmentator.cpp:268-288 (same stdout lines, file naming); the caller has started the CUDA context warm-up
+static int segment_one_file(const std::string& plyFile, float kthr, int segMinVerts, std::thread* warm) {
   printf("Segmenting %s with kThresh=%f, segMinVerts=%d ...\n", plyFile.c_str(), kthr, segMinVerts);
   const bool timing = getenv("SCN_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_start = now();
-  std::thread warm([]() { scn_cuda_warmup(); });          // context creation overlaps the file read
   float* xyz = nullptr; uint32_t* tri = nullptr; uint64_t nV = 0, nF = 0;
   const int load_rc = scn_mesh_load(plyFile.c_str(), &xyz, &nV, &tri, &nF);
-  warm.join();
+  if (warm && warm->joinable()) warm->join();
   if (load_rc) { std::cerr << scn_last_error() << std::endl; return 1; }
   printf("Read mesh with vertexCount %lu %lu, faceCount %lu %lu\n", (unsigned long)nV, (unsigned long)(nV * 3), (unsigned long)nF, (unsigned long)(nF * 3));
   const double t_loaded = now();
@@ -443,6 +436,39 @@ int scn_segmentator_main(int argc, const char** argv) {
   }
   printf("Segmentation written to %s with %lu segments\n", segFile.c_str(), (unsigned long)n_ids);
   return 0;
+}
+
+// `segmentator input.ply [kThresh] [segMinVerts]` as the reference; plus `segmentator --batch list.txt [kThresh] [segMinVerts]`:
+// every mesh named in list.txt (one path per line) in ONE process, so that the ~0.3 s of CUDA context creation - several
+// times the reference's whole run on a 50 k-vertex mesh - is paid once per batch instead of once per mesh
+// (Server/scan_processor.py:156 calls the tool once per scan; a batch is what a re-processing job wants).
+int scn_segmentator_main(int argc, const char** argv) {
+  if (argc < 2) {
+    printf("Usage: ./segmentator input.ply [kThresh] [segMinVerts] (defaults: kThresh=0.01 segMinVerts=20)\n");
+    return 255;                                                          // exit(-1)
+  }
+  std::thread warm([]() { scn_cuda_warmup(); });          // context creation overlaps the file read
+  if (!strcmp(argv[1], "--batch")) {
+    if (argc < 3) { warm.join(); printf("Usage: ./segmentator --batch list.txt [kThresh] [segMinVerts]\n"); return 255; }
+    const float kthr = argc > 3 ? (float)atof(argv[3]) : 0.01f;
+    const int segMinVerts = argc > 4 ? atoi(argv[4]) : 20;
+    std::ifstream lf(argv[2]);
+    if (!lf) { warm.join(); std::cerr << "cannot open " << argv[2] << std::endl; return 1; }
+    std::string line; int rc = 0;
+    while (std::getline(lf, line)) {
+      while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+      if (line.empty()) continue;
+      rc |= segment_one_file(line, kthr, segMinVerts, &warm);
+    }
+    if (warm.joinable()) warm.join();
+    return rc;
+  }
+  const std::string plyFile = argv[1];
+  const float kthr = argc > 2 ? (float)atof(argv[2]) : 0.01f;
+  const int segMinVerts = argc > 3 ? atoi(argv[3]) : 20;
+  const int rc = segment_one_file(plyFile, kthr, segMinVerts, &warm);
+  if (warm.joinable()) warm.join();
+  return rc;
 }
 
 int scn_mesh_save_ply(const char* path, const float* xyz, const uint8_t* rgb, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces) {

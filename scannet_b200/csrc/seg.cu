@@ -267,31 +267,35 @@ __global__ void k_sort_heap_fallback(Rec* __restrict__ A, const unsigned* __rest
 
 // tier 1 -----------------------------------------------------------------------------------------
 // per segment: median-of-3 to front (bits/stl_algo.h:1890-1900) and the number of tiles covering [s+1, e)
-__global__ void k_pivot(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
-                        unsigned nseg, unsigned* __restrict__ tileCnt) {
-  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nseg) return;
+__device__ __forceinline__ void d_pivot(unsigned g, Rec* A, const unsigned* segS, const unsigned* segE,
+                                        unsigned* tileCnt) {
   const long first = segS[g], last = segE[g];
   const long mid = first + (last - first) / 2;
   d_median_to_first(A + first, A + first + 1, A + mid, A + last - 1);
   tileCnt[g] = (unsigned)((last - first - 1 + kTile - 1) / kTile);
 }
+__global__ void k_pivot(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+                        unsigned nseg, unsigned* __restrict__ tileCnt) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nseg) d_pivot(g, A, segS, segE, tileCnt);
+}
 
-__device__ __forceinline__ unsigned find_seg(const unsigned* __restrict__ tileOff, unsigned nseg, unsigned tile) {
+__device__ __forceinline__ unsigned find_seg(const unsigned* tileOff, unsigned nseg, unsigned tile) {
   unsigned lo = 0, hi = nseg;                 // largest g with tileOff[g] <= tile
   while (hi - lo > 1) { const unsigned m = (lo + hi) >> 1; if (tileOff[m] <= tile) lo = m; else hi = m; }
   return lo;
 }
 
 struct TileCtx { unsigned g, s, e, t0; long base, end; float piv; };
-__device__ __forceinline__ TileCtx tile_ctx(const Rec* __restrict__ A, const unsigned* segS, const unsigned* segE,
-                                            const unsigned* tileOff, unsigned nseg) {
+__device__ __forceinline__ TileCtx tile_ctx(const Rec* A, const unsigned* segS, const unsigned* segE,
+                                            const unsigned* tileOff, unsigned nseg, unsigned tile) {
   __shared__ TileCtx sc;
+  __syncthreads();                                    // (the persistent kernel calls this in a loop: the previous tile's readers are done)
   if (threadIdx.x == 0) {
     TileCtx c;
-    c.g = find_seg(tileOff, nseg, blockIdx.x);
+    c.g = find_seg(tileOff, nseg, tile);
     c.s = segS[c.g]; c.e = segE[c.g]; c.t0 = tileOff[c.g];
-    c.base = (long)c.s + 1 + (long)(blockIdx.x - c.t0) * kTile;
+    c.base = (long)c.s + 1 + (long)(tile - c.t0) * kTile;
     c.end = min((long)c.e, c.base + kTile);
     c.piv = A[c.s].w;
     sc = c;
@@ -300,10 +304,9 @@ __device__ __forceinline__ TileCtx tile_ctx(const Rec* __restrict__ A, const uns
   return sc;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-k_count(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
-        const unsigned* __restrict__ tileOff, unsigned nseg, unsigned* __restrict__ tL, unsigned* __restrict__ tR) {
-  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+__device__ __forceinline__ void d_count(unsigned tile, const Rec* A, const unsigned* segS, const unsigned* segE,
+        const unsigned* tileOff, unsigned nseg, unsigned* tL, unsigned* tR) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg, tile);
   unsigned nl = 0, nr = 0;
   const long p0 = c.base + (long)threadIdx.x * kTileItems;
 #pragma unroll
@@ -314,18 +317,22 @@ k_count(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsi
   unsigned totl, totr;
   block_excl_scan(nl, &totl);
   block_excl_scan(nr, &totr);
-  if (threadIdx.x == 0) { tL[blockIdx.x] = totl; tR[blockIdx.x] = totr; }
+  if (threadIdx.x == 0) { tL[tile] = totl; tR[tile] = totr; }
+}
+__global__ void __launch_bounds__(kTileThreads)
+k_count(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+        const unsigned* __restrict__ tileOff, unsigned nseg, unsigned* __restrict__ tL, unsigned* __restrict__ tR) {
+  d_count(blockIdx.x, A, segS, segE, tileOff, nseg, tL, tR);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-k_scatter(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
-          const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
-          const unsigned* __restrict__ tR, unsigned* __restrict__ Lpos, unsigned* __restrict__ Rpos) {
-  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+__device__ __forceinline__ void d_scatter(unsigned tile, const Rec* A, const unsigned* segS, const unsigned* segE,
+          const unsigned* tileOff, unsigned nseg, const unsigned* gL, const unsigned* gR,
+          const unsigned* tR, unsigned* Lpos, unsigned* Rpos) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg, tile);
   const unsigned t1 = tileOff[c.g + 1];
-  const unsigned baseL = gL[blockIdx.x] - gL[c.t0];
+  const unsigned baseL = gL[tile] - gL[c.t0];
   const unsigned totR = gR[t1] - gR[c.t0];
-  const unsigned baseR = totR - (gR[blockIdx.x] - gR[c.t0]) - tR[blockIdx.x];     // right stoppers in later tiles
+  const unsigned baseR = totR - (gR[tile] - gR[c.t0]) - tR[tile];     // right stoppers in later tiles
   bool fl[kTileItems], fr[kTileItems];
   unsigned nl = 0, nr = 0;
   const long p0 = c.base + (long)threadIdx.x * kTileItems;
@@ -350,17 +357,22 @@ k_scatter(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const un
     if (fr[i]) { --rr_end; Rpos[c.s + rr_end] = (unsigned)p; }
   }
 }
+__global__ void __launch_bounds__(kTileThreads)
+k_scatter(const Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+          const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
+          const unsigned* __restrict__ tR, unsigned* __restrict__ Lpos, unsigned* __restrict__ Rpos) {
+  d_scatter(blockIdx.x, A, segS, segE, tileOff, nseg, gL, gR, tR, Lpos, Rpos);
+}
 
 // swaps + cut.  k-th pair (Lpos[s+k], Rpos[s+k]) swaps iff Lpos < Rpos; cut = min(L[m], R[m-1]).
-__global__ void __launch_bounds__(kTileThreads)
-k_swap(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
-       const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
-       const unsigned* __restrict__ Lpos, const unsigned* __restrict__ Rpos, unsigned* __restrict__ segCut) {
-  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg);
+__device__ __forceinline__ void d_swap_tile(unsigned tile, Rec* A, const unsigned* segS, const unsigned* segE,
+       const unsigned* tileOff, unsigned nseg, const unsigned* gL, const unsigned* gR,
+       const unsigned* Lpos, const unsigned* Rpos, unsigned* segCut) {
+  const TileCtx c = tile_ctx(A, segS, segE, tileOff, nseg, tile);
   const unsigned t1 = tileOff[c.g + 1];
   const unsigned nL = gL[t1] - gL[c.t0], nR = gR[t1] - gR[c.t0];
   const unsigned mn = min(nL, nR);
-  const unsigned k0 = (blockIdx.x - c.t0) * kTile + threadIdx.x * kTileItems;
+  const unsigned k0 = (tile - c.t0) * kTile + threadIdx.x * kTileItems;
 #pragma unroll
   for (int i = 0; i < kTileItems; ++i) {
     const unsigned k = k0 + i;
@@ -379,14 +391,18 @@ k_swap(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* _
     }
   }
 }
+__global__ void __launch_bounds__(kTileThreads)
+k_swap(Rec* __restrict__ A, const unsigned* __restrict__ segS, const unsigned* __restrict__ segE,
+       const unsigned* __restrict__ tileOff, unsigned nseg, const unsigned* __restrict__ gL, const unsigned* __restrict__ gR,
+       const unsigned* __restrict__ Lpos, const unsigned* __restrict__ Rpos, unsigned* __restrict__ segCut) {
+  d_swap_tile(blockIdx.x, A, segS, segE, tileOff, nseg, gL, gR, Lpos, Rpos, segCut);
+}
 
-__global__ void k_children(const unsigned* __restrict__ segS, const unsigned* __restrict__ segE, const unsigned* __restrict__ segD,
-                           const unsigned* __restrict__ segCut, unsigned nseg,
-                           unsigned* __restrict__ nS, unsigned* __restrict__ nE, unsigned* __restrict__ nD,
-                           unsigned* __restrict__ smStart, unsigned* __restrict__ smLenD,
-                           unsigned* __restrict__ hpStart, unsigned* __restrict__ hpEnd, SortCtl* __restrict__ ctl) {
-  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nseg) return;
+__device__ __forceinline__ void d_children(unsigned g, const unsigned* segS, const unsigned* segE, const unsigned* segD,
+                           const unsigned* segCut,
+                           unsigned* nS, unsigned* nE, unsigned* nD,
+                           unsigned* smStart, unsigned* smLenD,
+                           unsigned* hpStart, unsigned* hpEnd, SortCtl* ctl) {
   const unsigned s = segS[g], e = segE[g], cut = segCut[g], d = segD[g] - 1;
   const unsigned cs[2] = { s, cut }, ce[2] = { cut, e };
 #pragma unroll
@@ -397,6 +413,96 @@ __global__ void k_children(const unsigned* __restrict__ segS, const unsigned* __
     else if (d == 0) { const unsigned p = atomicAdd(&ctl->n_heap, 1u); hpStart[p] = cs[c]; hpEnd[p] = ce[c]; }
     else { const unsigned p = atomicAdd(&ctl->n_next, 1u); nS[p] = cs[c]; nE[p] = ce[c]; nD[p] = d; }
   }
+}
+__global__ void k_children(const unsigned* __restrict__ segS, const unsigned* __restrict__ segE, const unsigned* __restrict__ segD,
+                           const unsigned* __restrict__ segCut, unsigned nseg,
+                           unsigned* __restrict__ nS, unsigned* __restrict__ nE, unsigned* __restrict__ nD,
+                           unsigned* __restrict__ smStart, unsigned* __restrict__ smLenD,
+                           unsigned* __restrict__ hpStart, unsigned* __restrict__ hpEnd, SortCtl* __restrict__ ctl) {
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nseg) d_children(g, segS, segE, segD, segCut, nS, nE, nD, smStart, smLenD, hpStart, hpEnd, ctl);
+}
+
+// ---- the whole tier-1 loop as ONE persistent kernel ------------------------------------------------------------------
+// The level-synchronous partitioning used to be ~8 kernel launches and two host round trips (tile count, child count) per
+// level of the recursion tree - 254 launches for a 50 k-vertex mesh, launch- and sync-bound.  Here every resident CTA loops
+// over the levels itself: the phases of a level are separated by a grid-wide barrier (cooperative launch: all CTAs are
+// co-resident), tiles and segments are taken grid-stride, the three small scans of a level run inside one CTA, and the
+// loop ends on the device when no large segment is left.
+struct SortLevelsArgs {
+  Rec* A;
+  unsigned* seg[2];              // S | E | D, each maxLarge long
+  unsigned maxLarge;
+  unsigned* cut; unsigned* tileCnt; unsigned* tileOff; unsigned* tL; unsigned* tR; unsigned* gL; unsigned* gR;
+  unsigned* Lpos; unsigned* Rpos; unsigned* smStart; unsigned* smLenD; unsigned* hpStart; unsigned* hpEnd;
+  SortCtl* ctl; unsigned* bar;   // bar[0] arrivals, bar[1] generation, bar[2] levels done
+  unsigned nseg0;
+};
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned gen = *(volatile unsigned*)&bar[1];
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1) { bar[0] = 0; __threadfence(); atomicAdd(&bar[1], 1u); }
+    else { while (*(volatile unsigned*)&bar[1] == gen) { } }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// (none of the device functions above takes __restrict__ pointers: inside the persistent kernel these arrays are written by
+//  other CTAs between grid barriers, so their loads must stay coherent - no ld.global.nc)
+// exclusive scan of in[0..n) into out[0..n], out[n] = total, by ONE CTA of kTileThreads threads
+__device__ void cta_scan(const unsigned* in, unsigned* out, unsigned n) {
+  __shared__ unsigned s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (unsigned base = 0; base < n; base += kTile) {
+    unsigned v[kTileItems], sum = 0;
+    const unsigned p0 = base + threadIdx.x * kTileItems;
+#pragma unroll
+    for (int i = 0; i < kTileItems; ++i) { v[i] = p0 + i < n ? in[p0 + i] : 0u; sum += v[i]; }
+    unsigned tot;
+    unsigned ex = block_excl_scan(sum, &tot) + s_carry;
+#pragma unroll
+    for (int i = 0; i < kTileItems; ++i) { if (p0 + i < n) out[p0 + i] = ex; ex += v[i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = s_carry;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(kTileThreads)
+k_sort_levels(const SortLevelsArgs a) {
+  const unsigned nb = gridDim.x, gsz = nb * kTileThreads, gtid = blockIdx.x * kTileThreads + threadIdx.x;
+  unsigned nseg = a.nseg0, levels = 0;
+  int cur = 0;
+  while (nseg > 0) {
+    const unsigned* S = a.seg[cur]; const unsigned* E = S + a.maxLarge; const unsigned* D = S + 2 * a.maxLarge;
+    unsigned* NS = a.seg[cur ^ 1]; unsigned* NE = NS + a.maxLarge; unsigned* ND = NS + 2 * a.maxLarge;
+    for (unsigned g = gtid; g < nseg; g += gsz) d_pivot(g, a.A, S, E, a.tileCnt);
+    grid_barrier(a.bar, nb);
+    if (blockIdx.x == 0) cta_scan(a.tileCnt, a.tileOff, nseg);
+    grid_barrier(a.bar, nb);
+    const unsigned ntiles = *(volatile unsigned*)&a.tileOff[nseg];
+    for (unsigned t = blockIdx.x; t < ntiles; t += nb) d_count(t, a.A, S, E, a.tileOff, nseg, a.tL, a.tR);
+    grid_barrier(a.bar, nb);
+    if (blockIdx.x == 0) cta_scan(a.tL, a.gL, ntiles);
+    if (blockIdx.x == nb - 1) cta_scan(a.tR, a.gR, ntiles);
+    grid_barrier(a.bar, nb);
+    for (unsigned t = blockIdx.x; t < ntiles; t += nb) d_scatter(t, a.A, S, E, a.tileOff, nseg, a.gL, a.gR, a.tR, a.Lpos, a.Rpos);
+    grid_barrier(a.bar, nb);
+    for (unsigned t = blockIdx.x; t < ntiles; t += nb) d_swap_tile(t, a.A, S, E, a.tileOff, nseg, a.gL, a.gR, a.Lpos, a.Rpos, a.cut);
+    grid_barrier(a.bar, nb);
+    for (unsigned g = gtid; g < nseg; g += gsz) d_children(g, S, E, D, a.cut, NS, NE, ND, a.smStart, a.smLenD, a.hpStart, a.hpEnd, a.ctl);
+    grid_barrier(a.bar, nb);
+    nseg = *(volatile unsigned*)&a.ctl->n_next;
+    grid_barrier(a.bar, nb);                          // everyone has read n_next before it is cleared for the next level
+    if (gtid == 0) a.ctl->n_next = 0;
+    ++levels;
+    cur ^= 1;
+  }
+  if (gtid == 0) a.bar[2] = levels;
 }
 
 // ------------------------------------------------------------------------------ replay pruning
@@ -537,6 +643,36 @@ int device_introsort(Rec* A, size_t n, cudaStream_t st, int forced_depth = 0) {
     CK(cudaMemcpyAsync(S + maxLarge, &init[1], 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S + 2 * maxLarge, &init[2], 4, cudaMemcpyHostToDevice, st));
     nseg = 1;
+  }
+  static const bool by_launches = getenv("SCN_SEG_SORT_LAUNCHES") != nullptr;      // the per-level launch sequence, kept for A/B timing
+  if (nseg > 0 && !by_launches) {
+    // one cooperative launch runs every level (see k_sort_levels); grid = all co-resident CTAs
+    static thread_local int coop_blocks = 0;
+    if (!coop_blocks) {
+      int dev = 0, sms = 0, occ = 0, coop = 0;
+      CK(cudaGetDevice(&dev));
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_levels, kTileThreads, 0));
+      coop_blocks = coop ? sms * std::max(1, std::min(occ, 4)) : -1;
+    }
+    if (coop_blocks > 0) {
+      DevBuf bBar;
+      if (bBar.alloc(16)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc (sort barrier)");
+      CK(cudaMemsetAsync(bBar.p, 0, 16, st));
+      SortLevelsArgs a;
+      a.A = A; a.seg[0] = bSeg[0].as<unsigned>(); a.seg[1] = bSeg[1].as<unsigned>(); a.maxLarge = (unsigned)maxLarge;
+      a.cut = bCut.as<unsigned>(); a.tileCnt = bTileCnt.as<unsigned>(); a.tileOff = bTileOff.as<unsigned>();
+      a.tL = bTL.as<unsigned>(); a.tR = bTR.as<unsigned>(); a.gL = bGL.as<unsigned>(); a.gR = bGR.as<unsigned>();
+      a.Lpos = bLpos.as<unsigned>(); a.Rpos = bRpos.as<unsigned>(); a.smStart = smStart; a.smLenD = smLenD; a.hpStart = hpStart; a.hpEnd = hpEnd;
+      a.ctl = ctl; a.bar = bBar.as<unsigned>(); a.nseg0 = nseg;
+      void* params[] = { (void*)&a };
+      CK(cudaLaunchCooperativeKernel((const void*)k_sort_levels, dim3((unsigned)coop_blocks), dim3(kTileThreads), params, 0, st));
+      g_sort_launches += 1;
+      CK(cudaMemcpyAsync(&h, ctl, sizeof(SortCtl), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      nseg = 0;
+    }
   }
   while (nseg > 0) {
     unsigned* S = bSeg[cur].as<unsigned>(); unsigned* E = S + maxLarge; unsigned* D = S + 2 * maxLarge;
