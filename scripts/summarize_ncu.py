@@ -79,29 +79,55 @@ def main():
     tag = sys.argv[1]
     g = os.path.join(ROOT, "gpurun_out"); p = os.path.join(ROOT, "profiles"); os.makedirs(p, exist_ok=True)
     with open(os.path.join(p, f"{tag}_ncu_summary.md"), "w") as fh:
-        fh.write(f"# ncu summary {tag}\n\nCommand: see scripts/gpu_check.sh (bench.py --steps 2 --warmup 1 --frames-per-step 48 --no-cpu under ncu).\n\n")
+        fh.write(f"# ncu summary {tag}\n\nCommand: see scripts/gpu_r02b.sh (bench.py --steps 2 --warmup 1 --scene-frames 96 --frames-per-step 96 --no-cpu --no-seg under ncu).\n\n")
         lp = os.path.join(g, f"launches_{tag}.csv")
         if os.path.exists(lp):
             fh.write("## launch list (gpu__time_duration.sum, --clock-control none)\n\n"); summarize_launches(lp, fh)
         for f in sorted(os.listdir(g)):
             if f.endswith(f"_{tag}.ncu-rep"):
                 fh.write(f"## {f} (ncu --set full)\n\n"); summarize_rep(os.path.join(g, f), fh)
-    # DRAM traffic per launch of the dominant kernel, for bench.py's roofline.traffic
+    # per-kernel numbers bench.py quotes in its roofline block (profiles/latest_traffic.json)
     import json
-    tr = {}
+    tr = {}; issue = {}; inst = {}; mufu = {}
     for f in sorted(os.listdir(g)):
         if f.endswith(f"_{tag}.ncu-rep"):
-            rows = ncu_csv(os.path.join(g, f), "raw"); hdr = rows[0]
+            rep = os.path.join(g, f)
+            rows = ncu_csv(rep, "raw"); hdr = rows[0]
             for r in rows[2:]:
                 name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0]
                 def val(k):
-                    v = float(r[hdr.index(k)]); u = rows[1][hdr.index(k)]
+                    v = float(r[hdr.index(k)].replace(",", "")); u = rows[1][hdr.index(k)]
                     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 tr.setdefault(name, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+                if "smsp__issue_active.avg.pct_of_peak_sustained_active" in hdr:
+                    issue.setdefault(name, []).append(val("smsp__issue_active.avg.pct_of_peak_sustained_active"))
+                if "smsp__inst_executed.sum" in hdr:
+                    inst.setdefault(name, []).append(val("smsp__inst_executed.sum"))
+            # executed MUFU.RCP per launch = evaluated voxel-frames / 32 in the integrate kernels (one rcp per voxel-frame)
+            src = ncu_csv(rep, "source", ("--print-source", "sass"))
+            if len(src) > 2 and "k_integrate" in f.replace("prof_integrate", "k_integrate"):
+                hdr2 = src[1]
+                try:
+                    ia = hdr2.index("Instructions Executed"); isrc = hdr2.index("Source")
+                    c = Counter()
+                    for r in src[2:]:
+                        if len(r) == len(hdr2) and r[ia].isdigit():
+                            op = r[isrc].split(); o = (op[1] if op[0].startswith("@") else op[0]).split(".")[0]; c[o] += int(r[ia])
+                    if c.get("MUFU"):
+                        for name in list(inst):
+                            if name.startswith("k_integrate"):
+                                mufu[name] = sum(c.values()) / c["MUFU"]
+                except ValueError:
+                    pass
     if tr:
+        kint = next((k for k in tr if k.startswith("k_integrate")), None)
         with open(os.path.join(p, "latest_traffic.json"), "w") as fh:
-            json.dump({"tag": tag, "source": "ncu --set full, bench.py --steps 2 --warmup 1 --frames-per-step 48 (default batch)", "batch": 16,
-                       "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in tr.items()}}, fh, indent=1)
+            json.dump({"tag": tag, "source": "ncu --set full --clock-control none, bench.py --steps 2 --warmup 1 --scene-frames 96 --frames-per-step 96 (default batch)",
+                       "batch": 16, "integrate_kernel": kint,
+                       "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in tr.items()},
+                       "issue_active": {k: sum(v) / len(v) for k, v in issue.items()},
+                       "warp_inst_per_launch": {k: sum(v) / len(v) for k, v in inst.items()},
+                       "thread_inst_per_voxel_frame": mufu}, fh, indent=1)
     for f in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"gpu_{tag}.txt", f"pytest_gpu_{tag}.log", f"smoke_{tag}.log"):
         s = os.path.join(g, f)
         if os.path.exists(s):
