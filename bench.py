@@ -397,7 +397,7 @@ def make_sens_file(path, n_frames, seed, device, color_wh=(1296, 968), with_colo
         ok, buf = (True, None) if c is None else cv2.imencode(".jpg", c, [int(cv2.IMWRITE_JPEG_QUALITY), 85])
         return (b"" if c is None else buf.tobytes()), zlib.compress(d.tobytes(), 6)
 
-    with synth.SensWriter(path, n_frames, (W, H), (CW, CH) if with_color else (1, 1), sc.intrinsics(), Kc if with_color else None,
+    with synth.SensWriter(path, n_frames, (W, H), (CW, CH) if with_color else (0, 0), sc.intrinsics(), Kc if with_color else None,
                           color_comp=2 if with_color else 0) as wr, ThreadPoolExecutor(threads) as ex:
         for s0 in range(0, n_frames, chunk):
             Pc = P[s0:s0 + chunk]
@@ -410,7 +410,7 @@ def make_sens_file(path, n_frames, seed, device, color_wh=(1296, 968), with_colo
             else:
                 items = [(d[i], None) for i in range(len(Pc))]
             for i, (cb, db) in enumerate(ex.map(enc, items)):
-                wr.add(cb if with_color else bytes(3), db, Pc[i])
+                wr.add(cb if with_color else b"", db, Pc[i])
     return os.path.getsize(path), time.perf_counter() - t0
 
 
@@ -495,16 +495,16 @@ def main():
     grp = sdist.Group("nccl", dev)
 
     S, Wm = args.steps, args.warmup
-    SCENE_FRAMES = args.scene_frames
-    n_sc = max(1, args.frames_per_step // SCENE_FRAMES)
-    F = n_sc * SCENE_FRAMES
+    scene_frames = args.scene_frames
+    n_sc = max(1, args.frames_per_step // scene_frames)
+    F = n_sc * scene_frames
     frame_bytes = W * H * 2
     rgb_bytes = W * H * 3
     # every rank owns its own scenes (different sphere layouts per seed, same room size and camera loop, so the per-GPU work is
     # the same to within a few percent); every step replays them from an empty volume, so all steps do identical work
     scenes = []
     for j in range(n_sc):
-        sc, P = scene_poses(SCENE_FRAMES, sdist.scene_seed_for_rank(rank) * 16 + j, args.loop)
+        sc, P = scene_poses(scene_frames, sdist.scene_seed_for_rank(rank) * 16 + j, args.loop)
         d_depth = render_depth_torch(sc, P, dev)                                  # [1000,H,W] int16 (u16 bits), HBM resident
         h_depth = torch.empty(d_depth.shape, dtype=torch.int16, pin_memory=True)
         h_depth.copy_(d_depth)
@@ -553,7 +553,7 @@ def main():
             vol.sync(); vol.profile(True); acc["prof"] = True      # kernel timing events: timed steps only
         for sc in scenes:
             vol.reset()                                              # empty volume (clears only the blocks the last scene used)
-            vol.integrate_device(SCENE_FRAMES, sc["d"].data_ptr(), sc["dc"].data_ptr() if sc["dc"] is not None else None, sc["P"], sc["K"])
+            vol.integrate_device(scene_frames, sc["d"].data_ptr(), sc["dc"].data_ptr() if sc["dc"] is not None else None, sc["P"], sc["K"])
             if acc["collect"]:                                       # first (warm-up) step only: per-step counters, identical in every step
                 vol.sync(); st = vol.stats()
                 acc["nu"] += st.voxels_updated; acc["nb"] += st.blocks_visited; acc["blocks"] += st.blocks_allocated
@@ -573,7 +573,7 @@ def main():
     def step_e2e(s):
         for sc in scenes:
             vol2.reset()
-            vol2.integrate_batch_ptr(SCENE_FRAMES, sc["h"].data_ptr(), sc["hc"].data_ptr() if sc["hc"] is not None else None, sc["P"], sc["K"])
+            vol2.integrate_batch_ptr(scene_frames, sc["h"].data_ptr(), sc["hc"].data_ptr() if sc["hc"] is not None else None, sc["P"], sc["K"])
             vol2.stats()                                            # D2H read of the scene's result (counters)
 
     frames_all2, ms_e2e = timed(step_e2e)

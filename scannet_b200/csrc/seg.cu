@@ -818,7 +818,7 @@ k_kruskal_window(const Edge12* __restrict__ e, unsigned nE, UfElt* U, int* owner
       const int fa = owner[ra], fb = owner[rb];
       const float tha = U[ra].thr, thb = U[rb].thr;
       if (s_e[cur][fa].w > tha || s_e[cur][fb].w > thb) { /* a frozen component: rejected for good */ }
-      else if (fa == t && fb == t) merge = true;
+      else if (fa == t && fb == t) merge = ed.w <= tha && ed.w <= thb;      // the loop's own test (false for a NaN weight: rejected, retired)
       else keep = true;
     }
     __syncthreads();                                        // every read of the forest / owners precedes the writes below

@@ -38,7 +38,7 @@ def encode(img, q=85, sub=None, rst=0, gray=False, progressive=False):
     return buf.tobytes()
 
 
-def host_decode(tmp_path, jpegs, W, H, name="h.sens"):
+def host_decode(tmp_path, jpegs, W, H, name="h.sens", check_ref=True):
     """the product's host decoder (and the reference where it is built) through a .sens container"""
     D = np.full((len(jpegs), 8, 8), 1000, np.uint16); P = np.tile(np.eye(4, dtype=np.float32), (len(jpegs), 1, 1))
     p = str(tmp_path / name)
@@ -47,7 +47,7 @@ def host_decode(tmp_path, jpegs, W, H, name="h.sens"):
                      jpeg_encoder=lambda x: next(it))
     s = SensFile(p)
     out = np.stack([s.color(i) for i in range(len(jpegs))])
-    if os.path.exists(REF_SO):
+    if check_ref and os.path.exists(REF_SO):
         L = C.CDLL(REF_SO); L.ref_sens_open.restype = C.c_void_p; L.ref_sens_open.argtypes = [C.c_char_p]
         L.ref_sens_color.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]; L.ref_sens_close.argtypes = [C.c_void_p]
         r = L.ref_sens_open(p.encode()); rc = np.zeros((H, W, 3), np.uint8)
@@ -109,9 +109,9 @@ def test_streams_the_device_declines_go_through_the_host_decoder(tmp_path, built
 def test_corrupt_frames_behave_like_the_host_decoder(tmp_path, built):
     W, H = 96, 64
     good = encode(image(W, H, 5), 85, 0x221111)
-    cut = good[: len(good) * 2 // 3]                                          # truncated scan: stb (and the host decoder) still return an image
+    cut = good[: len(good) * 2 // 3]                                          # truncated scan: the host decoder still returns an image (stb reports "no EOI")
     wrong_size = encode(image(W + 8, H, 6), 85, 0x221111)                     # header says another size: an error on both paths
-    s, ref = host_decode(tmp_path, [good, cut], W, H)
+    s, ref = host_decode(tmp_path, [good, cut], W, H, check_ref=False)        # device path == host path of this library on damaged input
     out = torch.zeros((2, H, W, 3), dtype=torch.uint8, device="cuda")
     sens.jpeg_decode_batch_device([good, cut], W, H, out.data_ptr())
     assert (out.cpu().numpy() == ref).all()
