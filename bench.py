@@ -20,6 +20,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -299,8 +300,20 @@ def seg_bench(c5: bool):
                 if r.returncode == 0:
                     with open(os.path.join(d, "m.0.010000.segs.json")) as fh:
                         rec["bit_identical_to_reference"] = bool((np.array(json.load(fh)["segIndices"]) == seg).all())
+                ref0 = os.path.join(ROOT, "oracle", "_ref", "segmentator_ref")
+                if os.path.exists(ref0):            # the reference's own Makefile flags (-std=c++11, i.e. -O0; Segmentator/Makefile:1-5)
+                    t0 = time.perf_counter(); subprocess.run([ref0, p], capture_output=True, text=True); rec["cpu_reference_O0_s"] = time.perf_counter() - t0
                 t0 = time.perf_counter(); r2 = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "segmentator"), p], capture_output=True, text=True)
                 rec["gpu_cli_s"] = time.perf_counter() - t0
+                # the same mesh 8 times in ONE process (segmentator --batch): the CUDA context is paid once
+                lst = os.path.join(d, "list.txt")
+                paths = []
+                for q in range(8):
+                    pq = os.path.join(d, f"m{q}.ply"); shutil.copy(p, pq); paths.append(pq)
+                with open(lst, "w") as fh:
+                    fh.write("\n".join(paths) + "\n")
+                t0 = time.perf_counter(); r3 = subprocess.run([os.path.join(ROOT, "scannet_b200", "bin", "segmentator"), "--batch", lst], capture_output=True, text=True)
+                rec["gpu_cli_batch8_s_per_mesh"] = (time.perf_counter() - t0) / 8 if r3.returncode == 0 else None
         out[name] = rec
     return out
 
@@ -313,6 +326,7 @@ def sens_bench(n_frames=120):
     from scannet_b200 import synth
     from scannet_b200.sens import SensFile
     out = {}
+    ref_so_path = os.path.join(ROOT, "oracle", "_ref", "libref_sens.so")
     with tempfile.TemporaryDirectory() as d:
         sc, P = scene_poses(n_frames, 3, 1000)
         D = np.stack([sc.render(P[i], noise_mm=1.0, frame_seed=i)[0] for i in range(n_frames)])
@@ -361,6 +375,46 @@ def sens_bench(n_frames=120):
             for i in range(n_frames):
                 L.ref_sens_depth(r, i, buf.ctypes.data)
             out["reference_depth_decode_fps_1thread"] = n_frames / (time.perf_counter() - t0)
+        # colour (R4): JPEG 640x480 and 1296x968, host decoder 1 thread vs reference stb vs device decoder
+        try:
+            import cv2
+            import torch
+            from scannet_b200 import sens as _sens2
+            col = {}
+            for (cw, chh), reps in (((640, 480), 8), ((1296, 968), 4)):
+                imgs = []
+                yy, xx = np.mgrid[0:chh, 0:cw]
+                for i in range(24):
+                    im = np.stack([(xx * 255 // cw + 3 * i) % 256, (yy * 255 // chh + 5 * i) % 256, ((xx + yy) // 3 + 7 * i) % 256], -1).astype(np.uint8)
+                    im = cv2.GaussianBlur(im, (0, 0), 1.5)
+                    ok, buf = cv2.imencode(".jpg", im, [int(cv2.IMWRITE_JPEG_QUALITY), 85]); imgs.append(buf.tobytes())
+                pj = os.path.join(d, f"c{cw}.sens")
+                Dz = np.full((24, 8, 8), 1000, np.uint16); Pz = np.tile(np.eye(4, dtype=np.float32), (24, 1, 1)); it = iter(imgs)
+                synth.write_sens(pj, Dz, np.zeros((24, chh, cw, 3), np.uint8), Pz, np.eye(4, dtype=np.float32), depth_comp=0, color_comp=2, jpeg_encoder=lambda x: next(it))
+                sj = SensFile(pj)
+                t0 = time.perf_counter()
+                for i in range(24):
+                    sj.color(i)
+                rec = {"jpeg_bytes_per_frame": int(sum(len(b) for b in imgs) / 24), "host_decode_fps_1thread": 24 / (time.perf_counter() - t0)}
+                if os.path.exists(ref_so_path):
+                    Lr = C.CDLL(ref_so_path); Lr.ref_sens_open.restype = C.c_void_p; Lr.ref_sens_open.argtypes = [C.c_char_p]
+                    Lr.ref_sens_color.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+                    rr = Lr.ref_sens_open(pj.encode()); bufc = np.zeros((chh, cw, 3), np.uint8)
+                    t0 = time.perf_counter()
+                    for i in range(24):
+                        Lr.ref_sens_color(rr, i, bufc.ctypes.data)
+                    rec["reference_stb_decode_fps_1thread"] = 24 / (time.perf_counter() - t0)
+                jp = imgs * (reps * 10)
+                dout = torch.empty((len(jp), chh, cw, 3), dtype=torch.uint8, device="cuda")
+                _sens2.jpeg_decode_batch_device(jp[:24], cw, chh, dout.data_ptr())
+                t0 = time.perf_counter(); k = _sens2.jpeg_decode_batch_device(jp, cw, chh, dout.data_ptr()); dt = time.perf_counter() - t0
+                okc = bool((dout[-1].cpu().numpy() == sj.color(23)).all())
+                rec["device"] = {"frames": len(jp), "decoded_on_device": k, "fps_incl_parse_pack_h2d": len(jp) / dt, "ms": dt * 1e3, "identical_to_host_decode": okc}
+                col[f"{cw}x{chh}"] = rec
+                del dout
+            out["color_decode"] = col
+        except Exception as e:
+            out["color_decode"] = {"error": repr(e)}
         prm = os.path.join(d, "p.txt")
         with open(prm, "w") as fh:
             fh.write("s_SDFVoxelSize = 0.004f;\ns_SDFTruncation = 0.02f;\ns_SDFTruncationScale = 0.01f;\n")

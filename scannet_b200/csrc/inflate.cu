@@ -389,7 +389,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   InflateStage& g = g_stage;
   if (!g.ensure(tot + 16, n)) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: allocation of %zu staging bytes failed", tot);
   cudaError_t e = cudaMemcpyAsync(g.d_off, off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st);
-  const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  const unsigned nt = std::max(1u, std::min(24u, std::thread::hardware_concurrency()));     // packing is a 2-3 GB memcpy per scan: spread it
   int slot = 0; bool used[2] = {false, false};
   for (uint32_t i0 = 0; i0 < n && e == cudaSuccess;) {
     uint32_t i1 = i0; while (i1 < n && off[i1 + 1] - off[i0] <= kSlice) ++i1;               // streams [i0, i1) fit one slice

@@ -58,15 +58,32 @@ __constant__ unsigned char c_zig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11
 // (a marker stops the input: zero bits from then on)
 struct DevBits {
   const unsigned char* p; unsigned n, pos; unsigned buf; int cnt; bool hit_marker;
+  // two aligned 32-bit words of raw input held in registers, the second loaded one word early: the byte loads of fill()
+  // leave the dependent chain (p is 16-byte aligned: frames are packed at 16-byte offsets)
+  unsigned w0, w1;
+  __device__ __forceinline__ void window(unsigned at) {            // (re)load the two words covering byte `at`
+    const unsigned wi = at >> 2;
+    w0 = 4 * wi < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi) : 0u;
+    w1 = 4 * (wi + 1) < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi + 1) : 0u;
+  }
+  __device__ __forceinline__ unsigned byte_at(unsigned at) const {  // at in [pos, pos+1]: inside w0/w1 by construction
+    const unsigned w = ((at ^ pos) & ~3u) ? w1 : w0;              // another word than pos's -> the next one
+    return (w >> (8 * (at & 3u))) & 0xFFu;
+  }
+  __device__ __forceinline__ void advance(unsigned k) {            // k = 1 or 2
+    const unsigned np = pos + k;
+    if ((np ^ pos) & ~3u) { w0 = w1; const unsigned wi = (np >> 2) + 1; w1 = 4 * wi < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi) : 0u; }
+    pos = np;
+  }
   __device__ __forceinline__ void fill() {
     while (cnt <= 24) {
       unsigned b = 0;
       if (!hit_marker && pos < n) {
-        b = __ldg(p + pos);
+        b = byte_at(pos);
         if (b == 0xFFu) {
-          const unsigned nx = pos + 1 < n ? (unsigned)__ldg(p + pos + 1) : 0xD9u;
-          if (nx == 0) pos += 2; else { hit_marker = true; b = 0; }
-        } else ++pos;
+          const unsigned nx = pos + 1 < n ? byte_at(pos + 1) : 0xD9u;
+          if (nx == 0) advance(2); else { hit_marker = true; b = 0; }
+        } else advance(1);
       }
       buf |= b << (24 - cnt); cnt += 8;
     }
@@ -134,7 +151,8 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
   __syncwarp();
   const unsigned char* d = in + f.src_off;
   unsigned char* pl = planes + (size_t)blockIdx.x * plane_stride;
-  DevBits br{d, f.n_bytes, f.scan_start, 0u, 0, false};
+  DevBits br{d, f.n_bytes, f.scan_start, 0u, 0, false, 0u, 0u};
+  br.window(br.pos);
   int dc_pred[3] = {0, 0, 0};
   int todo = f.restart ? (int)f.restart : 0x7fffffff;
   int rc = JST_OK;
@@ -209,6 +227,7 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
         }
         if (bad || qpos + 1 >= f.n_bytes) { rc = (my == f.mcuy - 1 && mx == f.mcux - 1) ? JST_OK : JST_BAD_RESTART; my = f.mcuy; break; }   // the host stops decoding here too ("ended")
         br.pos = qpos + 2;
+        br.window(br.pos);
         dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
         todo = f.restart ? (int)f.restart : 0x7fffffff;
       }
@@ -459,7 +478,7 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
   if (e == cudaSuccess && !sets.empty()) e = cudaMemcpyAsync(g.d_sets, sets.data(), sets.size() * sizeof(TableSet), cudaMemcpyHostToDevice, st);
   // 2. pack + upload the supported payloads through the two pinned slices
   {
-    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned nt = std::max(1u, std::min(24u, std::thread::hardware_concurrency()));     // packing is a 2-3 GB memcpy per scan: spread it
     int slot = 0; bool used[2] = {false, false};
     for (uint32_t i0 = 0; i0 < n && e == cudaSuccess;) {
       uint32_t i1 = i0; while (i1 < n && off[i1 + 1] - off[i0] <= kJSlice) ++i1;
