@@ -185,6 +185,81 @@ SCN_HD uint32_t huff_decode(BitIn& b, const HuffTab& h, int mode) {
 
 enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_BAD_DIST = 4, INF_OUT_FULL = 5, INF_TRUNCATED = 6 };
 
+#ifdef __CUDA_ARCH__
+// ---- device-only symbol loop ---------------------------------------------------------------------------------------------------
+// A stream is ONE dependent chain of ~115-170 k symbols per frame, so what matters is the number of dependent instructions
+// per symbol.  The generic reader above (64-bit buffer, byte-wise refill loop) cost ~120 instructions per symbol; this one is
+// 32-bit throughout: three consecutive input words live in registers (the third loaded one word early), a funnel shift
+// extracts the next 32 bits at the current bit offset, one table entry carries code length, extra-bit count, kind and base
+// value, and literals / match lengths / distances are each decoded from a single peek.
+struct FastBits {
+  const uint32_t* p; uint32_t nwords, wi, w0, w1, w2, off;
+  __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < nwords ? __ldg(p + i) : 0u; }
+  __device__ __forceinline__ void init(const uint8_t* base, uint32_t n, uint32_t bitpos) {
+    p = reinterpret_cast<const uint32_t*>(base); nwords = (n + 3u) >> 2; wi = bitpos >> 5; off = bitpos & 31u;
+    w0 = ld(wi); w1 = ld(wi + 1); w2 = ld(wi + 2);
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, off); }
+  __device__ __forceinline__ void drop(uint32_t k) {                                       // k <= 28
+    off += k;
+    if (off >= 32u) { off -= 32u; w0 = w1; w1 = w2; ++wi; w2 = ld(wi + 2); }
+  }
+  __device__ __forceinline__ uint32_t bitpos() const { return (wi << 5) + off; }
+};
+__device__ __forceinline__ uint32_t long_code(const HuffTab& h, uint32_t win, int mode) {     // codes of 10..15 bits
+  const unsigned r = __brev(win & 0x7FFFu) >> 17;
+  for (int l = 10; l < 16; ++l) {
+    const unsigned c = (r >> (15 - l)) - h.first[l];
+    if (c < h.count[l]) return make_entry(mode, h.sym[h.offs[l] + c], (unsigned)l);
+  }
+  return K_BAD << 8;
+}
+// symbols of one Huffman block until its end-of-block code.  Returns INF_OK at EOB, INF_OUT_FULL when the frame is complete.
+__device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScratch& S, uint8_t* ring, uint8_t* out, uint32_t& o, uint32_t cap,
+                                                  int lane, uint32_t nbits) {
+  for (;;) {
+    uint32_t win = fb.peek();
+    uint32_t e = S.lit.fast[win & 511u];
+    if (!e) e = long_code(S.lit, win, M_LITLEN);
+    const uint32_t clen = e & 15u, kind = (e >> 8) & 3u;
+    if (kind == K_LIT) {
+      if (o >= cap) return fb.bitpos() > nbits ? INF_TRUNCATED : INF_OUT_FULL;                // (zero padding past a truncated stream decodes as literals)
+      fb.drop(clen);
+      if (lane == 0) { const uint8_t v = (uint8_t)(e >> 16); ring[o & (kWin - 1u)] = v; out[o] = v; }
+      ++o;
+      continue;
+    }
+    if (kind == K_EOB) { fb.drop(clen); return INF_OK; }
+    if (kind == K_BAD) return INF_BAD_CODE;
+    const uint32_t xb = (e >> 4) & 15u;
+    uint32_t len = (e >> 16) + ((win >> clen) & ((1u << xb) - 1u));                            // code + extra bits <= 20
+    fb.drop(clen + xb);
+    win = fb.peek();
+    uint32_t d = S.dist.fast[win & 511u];
+    if (!d) d = long_code(S.dist, win, M_DIST);
+    if (((d >> 8) & 3u) != K_BASE) return INF_BAD_CODE;
+    const uint32_t dl = d & 15u, dxb = (d >> 4) & 15u;                                          // code + extra bits <= 28
+    const uint32_t dist = (d >> 16) + ((win >> dl) & ((1u << dxb) - 1u));
+    fb.drop(dl + dxb);
+    if (fb.bitpos() > nbits) return INF_TRUNCATED;
+    if (dist > o) return INF_BAD_DIST;
+    const bool full = o + len > cap;
+    if (full) len = cap - o;                                                                     // the caller's frame is complete: write what fits and stop
+    __syncwarp();                                                                                // earlier literals / matches are visible to every lane
+    const uint32_t so = o - dist;
+    if (dist >= len) {
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + i) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+    } else if ((dist & (dist - 1u)) == 0u) {
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + (i & (dist - 1u))) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+    } else {
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + i % dist) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+    }
+    o += len;
+    if (full) return INF_OUT_FULL;
+  }
+}
+#endif
+
 // Inflates one zlib stream.  Every lane executes this with identical arguments except `lane`; the output is written
 // cooperatively.  Returns INF_* and the number of bytes produced.
 template <int LANES>
@@ -266,6 +341,20 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
         huff_build<LANES>(S.lit, lens, 288, lane, M_LITLEN); huff_build<LANES>(S.dist, lens + 288, 30, lane, M_DIST);
         lanes_sync<LANES>();
       }
+#ifdef __CUDA_ARCH__
+      if (LANES == 32 && (((size_t)in) & 3u) == 0u) {                 // the lean 32-bit symbol loop (streams are packed at 16-byte offsets)
+        if (b.over > 0) return INF_TRUNCATED;
+        FastBits fb;
+        fb.init(in, n, 8u * b.pos - (uint32_t)b.bc);                 // bytes before b.pos are in the bit buffer, b.bc of their bits still unread
+        const int frc = inflate_block_fast(fb, S, ring, out, o, cap, lane, 8u * n);
+        if (frc != INF_OK) { lanes_sync<LANES>(); *produced = o; return frc; }
+        const uint32_t bp = fb.bitpos();
+        if (bp > 8u * n) return INF_TRUNCATED;
+        bi_restart(b, bp >> 3); bi_refill(b); bi_drop(b, (int)(bp & 7u));
+        if (last) break;
+        continue;
+      }
+#endif
       for (;;) {
         bi_refill(b);
         const uint32_t e = huff_decode(b, S.lit, M_LITLEN);

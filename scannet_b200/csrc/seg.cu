@@ -444,7 +444,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
     __threadfence();
     const unsigned gen = *(volatile unsigned*)&bar[1];
     if (atomicAdd(&bar[0], 1u) == nblocks - 1) { bar[0] = 0; __threadfence(); atomicAdd(&bar[1], 1u); }
-    else { while (*(volatile unsigned*)&bar[1] == gen) { } }
+    else { while (*(volatile unsigned*)&bar[1] == gen) __nanosleep(40); }      // back off: hundreds of CTAs polling one line starve the arrivals
     __threadfence();
   }
   __syncthreads();
@@ -482,7 +482,7 @@ k_sort_levels(const SortLevelsArgs a) {
     unsigned* NS = a.seg[cur ^ 1]; unsigned* NE = NS + a.maxLarge; unsigned* ND = NS + 2 * a.maxLarge;
     for (unsigned g = gtid; g < nseg; g += gsz) d_pivot(g, a.A, S, E, a.tileCnt);
     grid_barrier(a.bar, nb);
-    if (blockIdx.x == 0) cta_scan(a.tileCnt, a.tileOff, nseg);
+    if (blockIdx.x == 0) { cta_scan(a.tileCnt, a.tileOff, nseg); if (threadIdx.x == 0) a.ctl->n_next = 0; }   // (all CTAs read n_next before the barrier above)
     grid_barrier(a.bar, nb);
     const unsigned ntiles = *(volatile unsigned*)&a.tileOff[nseg];
     for (unsigned t = blockIdx.x; t < ntiles; t += nb) d_count(t, a.A, S, E, a.tileOff, nseg, a.tL, a.tR);
@@ -497,10 +497,11 @@ k_sort_levels(const SortLevelsArgs a) {
     for (unsigned g = gtid; g < nseg; g += gsz) d_children(g, S, E, D, a.cut, NS, NE, ND, a.smStart, a.smLenD, a.hpStart, a.hpEnd, a.ctl);
     grid_barrier(a.bar, nb);
     nseg = *(volatile unsigned*)&a.ctl->n_next;
-    grid_barrier(a.bar, nb);                          // everyone has read n_next before it is cleared for the next level
-    if (gtid == 0) a.ctl->n_next = 0;
+    // n_next is re-armed by gtid 0 during the NEXT level's pivot phase (two barriers from here, and five before the next
+    // children phase adds to it) - every CTA has long read it by then
     ++levels;
     cur ^= 1;
+    if (nseg > 0 && gtid == 0) a.bar[3] = nseg;       // (kept for inspection: segments of the level about to start)
   }
   if (gtid == 0) a.bar[2] = levels;
 }
@@ -654,9 +655,11 @@ int device_introsort(Rec* A, size_t n, cudaStream_t st, int forced_depth = 0) {
       CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sort_levels, kTileThreads, 0));
-      coop_blocks = coop ? sms * std::max(1, std::min(occ, 4)) : -1;
+      coop_blocks = coop ? sms * std::max(1, std::min(occ, 2)) : -1;
     }
     if (coop_blocks > 0) {
+      // no more CTAs than the first level has tiles: a barrier costs with the number of CTAs that poll it
+      const int use_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)coop_blocks, (n + kTile - 1) / kTile));
       DevBuf bBar;
       if (bBar.alloc(16)) return scn::fail(SCN_ERR_CUDA, "cudaMalloc (sort barrier)");
       CK(cudaMemsetAsync(bBar.p, 0, 16, st));
@@ -667,7 +670,7 @@ int device_introsort(Rec* A, size_t n, cudaStream_t st, int forced_depth = 0) {
       a.Lpos = bLpos.as<unsigned>(); a.Rpos = bRpos.as<unsigned>(); a.smStart = smStart; a.smLenD = smLenD; a.hpStart = hpStart; a.hpEnd = hpEnd;
       a.ctl = ctl; a.bar = bBar.as<unsigned>(); a.nseg0 = nseg;
       void* params[] = { (void*)&a };
-      CK(cudaLaunchCooperativeKernel((const void*)k_sort_levels, dim3((unsigned)coop_blocks), dim3(kTileThreads), params, 0, st));
+      CK(cudaLaunchCooperativeKernel((const void*)k_sort_levels, dim3((unsigned)use_blocks), dim3(kTileThreads), params, 0, st));
       g_sort_launches += 1;
       CK(cudaMemcpyAsync(&h, ctl, sizeof(SortCtl), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
