@@ -523,7 +523,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=4000, help="rounded down to whole 1000-frame scenes (configs[1])")
     ap.add_argument("--scene-frames", type=int, default=SCENE_FRAMES, help="frames per synthetic scene (1000 = configs[1]; smaller only for profiler runs)")
-    ap.add_argument("--batch", type=int, default=16, help="frames fused per block residency (scn_tsdf_params.batch_frames)")
+    ap.add_argument("--batch", type=int, default=32, help="frames fused per block residency (scn_tsdf_params.batch_frames)")
     ap.add_argument("--loop", type=int, default=1000, help="frames per camera loop of the synthetic trajectory")
     ap.add_argument("--cpu-frames", type=int, default=24, help="bounded CPU sample: frames per reference step")
     ap.add_argument("--no-cpu", action="store_true")
@@ -533,7 +533,7 @@ def main():
     ap.add_argument("--tma-kernel", action="store_true", help="force the cp.async.bulk staged integrate kernel (SCN_TSDF_KERNEL_TMA)")
     ap.add_argument("--column-kernel", action="store_true", help="force the register-resident column kernel (SCN_TSDF_KERNEL_COLUMN)")
     ap.add_argument("--c3-frames", type=int, default=5578, help="frames of the configs[2] stand-in scan in the pipeline side section (0 = skip)")
-    ap.add_argument("--parity-frames", type=int, default=32, help="frames of the in-bench parity check against the oracle (0 = skip)")
+    ap.add_argument("--parity-frames", type=int, default=64, help="frames of the in-bench parity check against the oracle (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -121,7 +121,7 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
   scn_sens_info_t in; scn_sens_info(s, &in);
   scn_tsdf_params p = job.params;
   p.width = in.depth_width; p.height = in.depth_height; p.depth_shift = in.depth_shift;   // integrate at the stream's depth resolution
-  if (p.batch_frames == 0) p.batch_frames = 16;
+  if (p.batch_frames == 0) p.batch_frames = 32;
   const bool use_color = in.color_compression <= 2 && in.color_width > 0 && in.color_height > 0;   // raw, PNG, JPEG (sensorData.h:600-616)
   if (job.verbose)
     printf("fusing %s: %llu frames %ux%u, voxel %.4f m, truncation %.3f+%.3f*d\n", job.sens_path.c_str(), (unsigned long long)in.n_frames, in.depth_width,
@@ -359,7 +359,7 @@ int scn_fuse_main(int argc, const char** argv) {
   scn_tsdf_params p; scn_tsdf_default_params(&p);
   p.max_blocks = 1ull << 22; p.hash_slots = 1ull << 24;      // 16 GiB of voxel blocks unless the parameter file says otherwise (s_hashNumSDFBlocks)
   for (const std::string& f : params) if (scn_tsdf_params_from_file(f.c_str(), &p)) { fprintf(stderr, "%s\n", scn_last_error()); return 1; }
-  p.batch_frames = 16;
+  p.batch_frames = 32;
   const char* mode = getenv("SCN_FUSE_DECODE");
   if (scenes.size() == 1 && gpus <= 1) {
     SceneJob j; j.sens_path = scenes[0]; j.out_path = out_path.empty() ? default_out(scenes[0]) : out_path; j.params = p; j.device = 0; j.verbose = true; j.decode_mode = mode;

@@ -1,5 +1,5 @@
 """GPU parity at exactly the instantiation bench.py times:
-640x480, 4 mm voxels, K = 16 frames per block residency, depth-only (constant sample weight, stats on), >= 4 batches in
+640x480, 4 mm voxels, K = 32 frames per block residency (bench.py --batch default; K = 16 in the colour case), depth-only (constant sample weight, stats on), >= 4 batches in
 flight so the alloc(k+1) || integrate(k) double buffering is exercised — through BOTH scn_tsdf_integrate_device (frames
 resident in HBM) and scn_tsdf_integrate_batch (pinned host frames), plus a colour K=16 case and a reset-and-refuse case.
 Tolerance ZERO against oracle/tsdf_oracle.c (own spec, parity unpinned — the reference has no TSDF source)."""
@@ -45,9 +45,9 @@ def check(vol, ox, ov, oc):
 @pytest.mark.timeout(600)
 def test_bench_instantiation_device_and_pinned_batch(built):
     import torch
-    n = 80                                                     # 5 batches of 16
+    n = 144                                                    # 4.5 batches of 32
     D, _, P, K = frames(n, seed=0)
-    p = tsdf.default_params(batch_frames=16, max_blocks=1 << 18, hash_slots=1 << 20)     # bench.py's flags (0: stats on)
+    p = tsdf.default_params(batch_frames=32, max_blocks=1 << 18, hash_slots=1 << 20)     # bench.py's parameters and flags (0: stats on)
     ox, ov, oc = oracle_run(p, D, None, P, K)
     # (1) frames resident in HBM -> scn_tsdf_integrate_device, launched on torch's stream like bench.py
     d = torch.from_numpy(D.view(np.int16)).cuda()
@@ -72,12 +72,12 @@ def test_bench_instantiation_split_calls_and_ragged_tail(built):
     import torch
     n = 64
     D, _, P, K = frames(n, seed=3)
-    p = tsdf.default_params(batch_frames=16, max_blocks=1 << 18, hash_slots=1 << 20)
+    p = tsdf.default_params(batch_frames=32, max_blocks=1 << 18, hash_slots=1 << 20)
     ox, ov, oc = oracle_run(p, D, None, P, K)
     d = torch.from_numpy(D.view(np.int16)).cuda()
     vol = tsdf.TsdfVolume(p, device=0, stream=torch.cuda.current_stream().cuda_stream)
     o = 0
-    for cnt in (37, 1, 26):
+    for cnt in (37, 1, 26):                                   # 32 + 5 | 1 | 26: partial batches between calls
         vol.integrate_device(cnt, d.data_ptr() + o * W * H * 2, None, P[o:o + cnt], K)
         o += cnt
     check(vol, ox, ov, oc)
@@ -105,9 +105,9 @@ def test_bench_instantiation_colour_k16(built):
 def test_bench_instantiation_no_stats_flag(built):
     """SCN_TSDF_NO_STATS compiles a different kernel instantiation: same voxels"""
     import torch
-    n = 32
+    n = 64
     D, _, P, K = frames(n, seed=5)
-    p = tsdf.default_params(batch_frames=16, max_blocks=1 << 18, hash_slots=1 << 20, flags=tsdf.NO_STATS)
+    p = tsdf.default_params(batch_frames=32, max_blocks=1 << 18, hash_slots=1 << 20, flags=tsdf.NO_STATS)
     ox, ov, _ = oracle_run(p, D, None, P, K)
     d = torch.from_numpy(D.view(np.int16)).cuda()
     vol = tsdf.TsdfVolume(p, device=0, stream=torch.cuda.current_stream().cuda_stream)
