@@ -140,6 +140,8 @@ int  scn_sens_frame_payload(const scn_sens* s, uint64_t frame, const uint8_t** c
  * cudaStream_t (0 = default); returns after the work has completed. */
 int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_bytes, uint32_t n, uint32_t width, uint32_t height,
                                  const int32_t* d_lut, uint32_t out_px, void* d_out, void* stream, uint32_t* n_on_device);
+/* timings of the calling thread's last scn_jpeg_decode_batch_device: host parse + pack + upload issue (s), entropy+IDCT kernel (ms), colour kernel (ms) */
+int scn_jpeg_last_timings(double* host_s, double* entropy_ms, double* color_ms);
 /* colour frames [first, first+n) of an open stream into device memory (JPEG on the GPU; raw / PNG via the host decoder) */
 int scn_sens_decode_color_device(const scn_sens* s, uint64_t first, uint32_t n, const int32_t* d_lut, uint32_t out_px, void* d_out,
                                  void* stream, uint32_t* n_on_device);
@@ -297,6 +299,9 @@ int  scn_sens_decode_depth_device(const scn_sens* s, uint64_t first_frame, uint3
 /* the same for caller-supplied zlib streams: src[i] / src_bytes[i] on the host, each must inflate to >= frame_bytes */
 int  scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_bytes, uint32_t n, uint64_t frame_bytes, void* d_out,
                               void* stream);
+/* timings of the calling thread's last scn_inflate_batch_device: host packing + upload issue (s), kernel (ms, CUDA events), whether
+ * the shared-memory-window kernel ran (else the window lives in HBM), streams in the launch */
+int  scn_inflate_last_timings(double* pack_s, double* kernel_ms, int* ring_window, uint32_t* n_streams);
 /* host build of the same decoder source (one lane): used by the CPU test-suite; not a product path */
 int  scn_inflate_host(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* produced);
 

@@ -142,7 +142,7 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
   auto fail_here = [&](const char* what) { if (!rc) { rc = 1; err = what && *what ? what : scn_last_error(); } };
   if (gpu_decode) {
     const char* ce = getenv("SCN_FUSE_CHUNK");
-    const uint32_t CH = (uint32_t)std::max(16, std::min(4096, ce ? atoi(ce) : 512));
+    const uint32_t CH = (uint32_t)std::max(16, std::min(4096, ce ? atoi(ce) : 1024));   // frames per decode chunk: enough streams in flight for the one-warp-per-frame decoders
     const uint64_t n_chunks = (in.n_frames + CH - 1) / CH;
     uint16_t* d_depth[2] = {nullptr, nullptr}; uint8_t* d_rgb[2] = {nullptr, nullptr}; int32_t* d_lut = nullptr;
     void* st_d = nullptr; void* st_c = nullptr;

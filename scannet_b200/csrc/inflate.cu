@@ -18,6 +18,7 @@
 // copied.  The same source compiles for the host (one lane, no ring) so the decoder is unit-tested on the CPU against
 // zlib streams of every block type.
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -46,7 +47,7 @@ struct InflateScratchDev { uint8_t ring[kWin]; InflateScratch s; };
 // re-derive the shared window for every symbol.
 extern __shared__ __align__(16) unsigned char g_inflate_smem[];
 #ifdef __CUDA_ARCH__
-#define SCN_SCR(scr) (reinterpret_cast<InflateScratchDev*>(g_inflate_smem)->s)
+#define SCN_SCR(scr) (RING ? reinterpret_cast<InflateScratchDev*>(g_inflate_smem)->s : *reinterpret_cast<InflateScratch*>(g_inflate_smem))
 #define SCN_RING (reinterpret_cast<InflateScratchDev*>(g_inflate_smem)->ring)
 #else
 #define SCN_SCR(scr) (*(scr))
@@ -215,8 +216,12 @@ __device__ __forceinline__ uint32_t long_code(const HuffTab& h, uint32_t win, in
   return K_BAD << 8;
 }
 // symbols of one Huffman block until its end-of-block code.  Returns INF_OK at EOB, INF_OUT_FULL when the frame is complete.
+// RING: the window is the shared-memory ring (+ a copy of every byte streamed to HBM); !RING: the window is the output in HBM
+template <bool RING>
 __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScratch& S, uint8_t* ring, uint8_t* out, uint32_t& o, uint32_t cap,
                                                   int lane, uint32_t nbits) {
+  uint8_t* const wbase = RING ? ring : out;
+  const uint32_t wmask = RING ? kWin - 1u : 0xFFFFFFFFu;
   for (;;) {
     uint32_t win = fb.peek();
     uint32_t e = S.lit.fast[win & 511u];
@@ -225,7 +230,7 @@ __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScr
     if (kind == K_LIT) {
       if (o >= cap) return fb.bitpos() > nbits ? INF_TRUNCATED : INF_OUT_FULL;                // (zero padding past a truncated stream decodes as literals)
       fb.drop(clen);
-      if (lane == 0) { const uint8_t v = (uint8_t)(e >> 16); ring[o & (kWin - 1u)] = v; out[o] = v; }
+      if (lane == 0) { const uint8_t v = (uint8_t)(e >> 16); if (RING) ring[o & (kWin - 1u)] = v; out[o] = v; }
       ++o;
       continue;
     }
@@ -248,11 +253,11 @@ __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScr
     __syncwarp();                                                                                // earlier literals / matches are visible to every lane
     const uint32_t so = o - dist;
     if (dist >= len) {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + i) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + i) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
     } else if ((dist & (dist - 1u)) == 0u) {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + (i & (dist - 1u))) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + (i & (dist - 1u))) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
     } else {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = ring[(so + i % dist) & (kWin - 1u)]; ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + i % dist) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
     }
     o += len;
     if (full) return INF_OUT_FULL;
@@ -262,7 +267,7 @@ __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScr
 
 // Inflates one zlib stream.  Every lane executes this with identical arguments except `lane`; the output is written
 // cooperatively.  Returns INF_* and the number of bytes produced.
-template <int LANES>
+template <int LANES, bool RING>
 SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap_in, int lane, InflateScratch* scr, size_t* produced) {
   *produced = 0;
   if (n_in < 2 || n_in > 0xFFFFFFF0ull || cap_in > 0xFFFFFFF0ull) return INF_BAD_HEADER;
@@ -274,9 +279,9 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
   uint32_t o = 0;
   // device: every output byte goes to the shared-memory ring (what later matches read) and to HBM; host: straight to `out`
 #ifdef __CUDA_ARCH__
-  uint8_t* const ring = SCN_RING;
-#define SCN_PUT(idx, v) do { const uint8_t v_ = (v); ring[(idx) & (kWin - 1u)] = v_; out[(idx)] = v_; } while (0)
-#define SCN_WIN(idx) ring[(idx) & (kWin - 1u)]
+  uint8_t* const ring = RING ? SCN_RING : nullptr;
+#define SCN_PUT(idx, v) do { const uint8_t v_ = (v); if (RING) ring[(idx) & (kWin - 1u)] = v_; out[(idx)] = v_; } while (0)
+#define SCN_WIN(idx) (RING ? ring[(idx) & (kWin - 1u)] : out[(idx)])
 #else
 #define SCN_PUT(idx, v) out[(idx)] = (v)
 #define SCN_WIN(idx) out[(idx)]
@@ -346,7 +351,7 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
         if (b.over > 0) return INF_TRUNCATED;
         FastBits fb;
         fb.init(in, n, 8u * b.pos - (uint32_t)b.bc);                 // bytes before b.pos are in the bit buffer, b.bc of their bits still unread
-        const int frc = inflate_block_fast(fb, S, ring, out, o, cap, lane, 8u * n);
+        const int frc = inflate_block_fast<RING>(fb, S, ring, out, o, cap, lane, 8u * n);
         if (frc != INF_OK) { lanes_sync<LANES>(); *produced = o; return frc; }
         const uint32_t bp = fb.bitpos();
         if (bp > 8u * n) return INF_TRUNCATED;
@@ -396,13 +401,14 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
 }
 
 // one warp per stream
+template <bool RING>
 __global__ void __launch_bounds__(32) k_inflate(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ in_off, uint8_t* out,
                                                   size_t out_stride, size_t out_cap, unsigned n, int* __restrict__ status,
                                                   unsigned long long* __restrict__ produced) {
   const unsigned s = blockIdx.x;
   if (s >= n) return;
   size_t got = 0;
-  const int rc = inflate_zlib<32>(in + in_off[s], (size_t)(in_off[s + 1] - in_off[s]), out + (size_t)s * out_stride, out_cap, (int)threadIdx.x, nullptr, &got);
+  const int rc = inflate_zlib<32, RING>(in + in_off[s], (size_t)(in_off[s + 1] - in_off[s]), out + (size_t)s * out_stride, out_cap, (int)threadIdx.x, nullptr, &got);
   if (threadIdx.x == 0) { status[s] = rc; produced[s] = got; }
 }
 
@@ -419,15 +425,18 @@ const char* inf_msg(int rc) {
 constexpr size_t kSlice = size_t(64) << 20;
 struct InflateStage {
   uint8_t* h[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t tk[2] = {nullptr, nullptr};            // timing events around the kernel
+  double last_pack_s = 0, last_kernel_ms = 0; int last_ring = 0; unsigned last_n = 0;
   uint8_t* d = nullptr; size_t cap = 0;
   unsigned long long* d_off = nullptr; int* d_status = nullptr; unsigned long long* d_prod = nullptr; size_t ncap = 0;
   void release() {
-    for (int i = 0; i < 2; ++i) { if (h[i]) cudaFreeHost(h[i]); h[i] = nullptr; if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) { if (h[i]) cudaFreeHost(h[i]); h[i] = nullptr; if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; if (tk[i]) cudaEventDestroy(tk[i]); tk[i] = nullptr; }
     cudaFree(d); cudaFree(d_off); cudaFree(d_status); cudaFree(d_prod); d = nullptr; d_off = d_prod = nullptr; d_status = nullptr; cap = ncap = 0;
   }
   bool ensure(size_t bytes, size_t n) {
     for (int i = 0; i < 2; ++i) if (!h[i]) {
-      if (cudaHostAlloc((void**)&h[i], kSlice, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+      if (cudaHostAlloc((void**)&h[i], kSlice, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreate(&tk[i]) != cudaSuccess) { cudaGetLastError(); release(); return false; }
     }
     if (bytes > cap) {
       cudaFree(d); d = nullptr; cap = 0;
@@ -454,7 +463,7 @@ extern "C" {
 int scn_inflate_host(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* produced) {
   if (!src || !out || !produced) return scn::fail(SCN_ERR_ARG, "null argument");
   std::vector<InflateScratch> scr(1);
-  const int rc = inflate_zlib<1>(src, n, out, cap, 0, scr.data(), produced);
+  const int rc = inflate_zlib<1, false>(src, n, out, cap, 0, scr.data(), produced);
   return rc == INF_OK ? SCN_OK : scn::fail(SCN_ERR_FORMAT, "inflate: %s", inf_msg(rc));
 }
 
@@ -467,6 +476,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   if (!n) return SCN_OK;
   if (!src || !src_bytes || !d_out) return scn::fail(SCN_ERR_ARG, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  const double t_call = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   std::vector<unsigned long long> off((size_t)n + 1);
   size_t tot = 0;
   for (uint32_t i = 0; i < n; ++i) {
@@ -498,18 +508,38 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
     used[slot] = true; slot ^= 1; i0 = i1;
   }
   std::vector<int> status(n); std::vector<unsigned long long> prod(n);
+  const double t_packed = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  // Window placement.  Shared-memory ring: ~2.5x lower latency per stream, but 38.5 KB per stream = 5 streams per SM; window in
+  // HBM (matches read the output back through L2): 32 streams per SM.  Up to about two waves of ring streams the ring wins.
+  static const int n_sm = []() { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  const char* wenv = getenv("SCN_INFLATE_WINDOW");
+  const bool use_ring = wenv ? !strcmp(wenv, "ring") : n <= (uint32_t)(10 * n_sm);
   if (e == cudaSuccess) {
-    k_inflate<<<n, 32, sizeof(InflateScratchDev), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    cudaEventRecord(g.tk[0], st);
+    if (use_ring) k_inflate<true><<<n, 32, sizeof(InflateScratchDev), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    else k_inflate<false><<<n, 32, sizeof(InflateScratch), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);
+    cudaEventRecord(g.tk[1], st);
     e = cudaMemcpyAsync(status.data(), g.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(prod.data(), g.d_prod, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: %s", cudaGetErrorString(e));
+  { float ms = 0; if (cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g.last_kernel_ms = ms; g.last_pack_s = t_packed - t_call; g.last_ring = use_ring; g.last_n = n; }
   for (uint32_t i = 0; i < n; ++i) {
     if (status[i] != INF_OK && status[i] != INF_OUT_FULL) return scn::fail(SCN_ERR_FORMAT, "frame %u: corrupt zlib depth stream (%s)", i, inf_msg(status[i]));
     if (prod[i] < frame_bytes) return scn::fail(SCN_ERR_FORMAT, "frame %u: depth stream holds %llu bytes, need %llu", i, prod[i], (unsigned long long)frame_bytes);
   }
+  return SCN_OK;
+}
+
+// timings of the last scn_inflate_batch_device call of this thread: host packing + upload issue (s), inflate kernel (ms, CUDA
+// events), whether the shared-memory-window kernel ran, streams in the launch
+int scn_inflate_last_timings(double* pack_s, double* kernel_ms, int* ring_window, uint32_t* n_streams) {
+  if (pack_s) *pack_s = g_stage.last_pack_s;
+  if (kernel_ms) *kernel_ms = g_stage.last_kernel_ms;
+  if (ring_window) *ring_window = g_stage.last_ring;
+  if (n_streams) *n_streams = g_stage.last_n;
   return SCN_OK;
 }
 

@@ -19,6 +19,7 @@
 // else (progressive, multi-scan, exotic sampling) and every frame the device flags as corrupt is decoded by the host
 // decoder (jpeg.cpp) and uploaded - same bytes, same errors.
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -54,53 +55,93 @@ __constant__ unsigned char c_zig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11
                                              29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63,
                                              63,63,63,63,63,63,63,63,63,63,63,63,63,63,63};
 
-// MSB-first bit reader over the entropy-coded segment with JPEG byte stuffing, same state machine as jpeg.cpp's `Bits`
-// (a marker stops the input: zero bits from then on)
-struct DevBits {
-  const unsigned char* p; unsigned n, pos; unsigned buf; int cnt; bool hit_marker;
-  // two aligned 32-bit words of raw input held in registers, the second loaded one word early: the byte loads of fill()
-  // leave the dependent chain (p is 16-byte aligned: frames are packed at 16-byte offsets)
-  unsigned w0, w1;
-  __device__ __forceinline__ void window(unsigned at) {            // (re)load the two words covering byte `at`
-    const unsigned wi = at >> 2;
-    w0 = 4 * wi < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi) : 0u;
-    w1 = 4 * (wi + 1) < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi + 1) : 0u;
+// MSB-first bit reader over the entropy-coded segment, same bit stream as jpeg.cpp's `Bits` (byte stuffing removed, a marker
+// stops the input: zero bits from then on) - but the stuffing is removed by the WHOLE WARP, 32 raw bytes per step (ballot +
+// prefix count compaction into a 1 KB ring in shared memory), so the bit-serial chain only ever sees clean big-endian words:
+// one funnel shift per peek, one shared-memory load per 32 bits.  The first version (byte-wise refill with the FF test on
+// the dependent chain) cost ~600 cycles per symbol.
+constexpr unsigned kCleanRing = 1024;
+struct CleanBits {
+  const unsigned char* p; unsigned n;       // raw stream
+  unsigned char* ring;                      // shared memory, kCleanRing bytes, 4-byte aligned
+  unsigned raw_pos;                         // next raw byte to stage
+  unsigned fill, used;                      // clean bytes staged / fetched so far (monotone)
+  unsigned w0, w1, off;                     // the two big-endian words at the read position, bit offset into w0
+  unsigned last_raw;                        // raw byte before raw_pos (an FF there makes a following 00 a stuffed byte)
+  unsigned marker_pos; bool marker;         // a marker (FF xx, xx != 0) stopped the staging at marker_pos
+  int lane;
+
+  __device__ __forceinline__ void stage32() {          // all lanes: up to 32 raw bytes -> ring
+    const unsigned r = raw_pos + (unsigned)lane;
+    const bool valid = r < n;
+    const unsigned b = valid ? (unsigned)__ldg(p + r) : 0x100u;
+    unsigned nxt = __shfl_down_sync(0xffffffffu, b, 1);
+    if (lane == 31) nxt = r + 1 < n ? (unsigned)__ldg(p + r + 1) : 0xD9u;
+    if (valid && r + 1 >= n) nxt = 0xD9u;                // the host treats the byte after the last one as EOI
+    unsigned prv = __shfl_up_sync(0xffffffffu, b, 1);
+    if (lane == 0) prv = last_raw;
+    const bool is_mark = valid && b == 0xFFu && nxt != 0u;
+    const bool is_stuff = valid && b == 0u && prv == 0xFFu;
+    const unsigned mm = __ballot_sync(0xffffffffu, is_mark);
+    const unsigned first = mm ? (unsigned)__ffs(mm) - 1u : 32u;
+    const unsigned nvalid = min(32u, n - raw_pos);
+    const unsigned stop = min(first, nvalid);
+    const bool emit = (unsigned)lane < stop && !is_stuff;
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (emit) ring[(fill + __popc(em & ((1u << lane) - 1u))) & (kCleanRing - 1u)] = (unsigned char)b;
+    fill += __popc(em);
+    if (stop) last_raw = __shfl_sync(0xffffffffu, b, (int)stop - 1);
+    raw_pos += stop;
+    if (first < nvalid) { marker = true; marker_pos = raw_pos; }
+    __syncwarp();
   }
-  __device__ __forceinline__ unsigned byte_at(unsigned at) const {  // at in [pos, pos+1]: inside w0/w1 by construction
-    const unsigned w = ((at ^ pos) & ~3u) ? w1 : w0;              // another word than pos's -> the next one
-    return (w >> (8 * (at & 3u))) & 0xFFu;
+  __device__ __forceinline__ void refill() {           // keep the ring ahead of the reader
+    while (!marker && raw_pos < n && (int)(fill - used) <= (int)(kCleanRing - 64u)) stage32();
   }
-  __device__ __forceinline__ void advance(unsigned k) {            // k = 1 or 2
-    const unsigned np = pos + k;
-    if ((np ^ pos) & ~3u) { w0 = w1; const unsigned wi = (np >> 2) + 1; w1 = 4 * wi < n ? __ldg(reinterpret_cast<const unsigned*>(p) + wi) : 0u; }
-    pos = np;
-  }
-  __device__ __forceinline__ void fill() {
-    while (cnt <= 24) {
-      unsigned b = 0;
-      if (!hit_marker && pos < n) {
-        b = byte_at(pos);
-        if (b == 0xFFu) {
-          const unsigned nx = pos + 1 < n ? byte_at(pos + 1) : 0xD9u;
-          if (nx == 0) advance(2); else { hit_marker = true; b = 0; }
-        } else advance(1);
-      }
-      buf |= b << (24 - cnt); cnt += 8;
+  __device__ __forceinline__ unsigned fetch() {        // next 4 clean bytes, big endian; zeros past a marker / the end
+    if ((int)(fill - used) < 4) refill();
+    unsigned w;
+    if ((int)(fill - used) >= 4) w = __byte_perm(*reinterpret_cast<const unsigned*>(ring + (used & (kCleanRing - 1u))), 0u, 0x0123);
+    else {
+      w = 0u;
+      for (int i = 0; i < 4; ++i) if ((int)(fill - used) > i) w |= (unsigned)ring[(used + i) & (kCleanRing - 1u)] << (24 - 8 * i);
     }
+    used += 4u;
+    return w;
   }
-  __device__ __forceinline__ int get(int k) { if (k == 0) return 0; if (cnt < k) fill(); const int v = (int)(buf >> (32 - k)); buf <<= k; cnt -= k; return v; }
+  __device__ __forceinline__ void start(unsigned at) {
+    raw_pos = at; fill = used = 0u; last_raw = 0u; marker = false; marker_pos = 0u; off = 0u;
+    refill();
+    w0 = fetch(); w1 = fetch();
+  }
+  __device__ __forceinline__ unsigned peek() const { return __funnelshift_l(w1, w0, off); }      // 32 bits at the read position
+  __device__ __forceinline__ void consume(unsigned k) {                                           // k <= 16
+    off += k;
+    if (off >= 32u) { off -= 32u; w0 = w1; w1 = fetch(); }
+  }
+  __device__ __forceinline__ int get(int k) { if (k == 0) return 0; const int v = (int)(peek() >> (32 - k)); consume((unsigned)k); return v; }
   __device__ __forceinline__ int decode(const HuffTab& h) {
-    if (cnt < 16) fill();
-    const unsigned e = h.fast[buf >> (32 - kFastBits)];
-    if (e != 0xFFFFu) { const int l = e & 15; buf <<= l; cnt -= l; return (int)(e >> 4); }
-    int code = 0;
-    for (int l = 1; l <= 16; ++l) {
-      code = (code << 1) | (int)(buf >> 31); buf <<= 1; --cnt;
-      if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+    const unsigned pk = peek();
+    const unsigned e = h.fast[pk >> (32 - kFastBits)];
+    if (e != 0xFFFFu) { consume(e & 15u); return (int)(e >> 4); }
+    for (int l = 1; l <= 16; ++l) {                     // jpeg.cpp consumes these bits one at a time: same codes, same count
+      const int code = (int)(pk >> (32 - l));
+      if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) { consume((unsigned)l); return h.vals[h.valptr[l] + code - h.mincode[l]]; }
     }
+    consume(16u);
     return -1;
   }
-  __device__ __forceinline__ void reset() { buf = 0; cnt = 0; hit_marker = false; }
+  // restart interval boundary (jpeg.cpp: handle_restart).  Returns 1 = continue after RSTn, 0 = the scan ends here
+  // (as the host decoder decides when no RSTn follows).
+  __device__ __forceinline__ int restart() {
+    while (!marker && raw_pos < n) { fill = used; stage32(); }                                   // discard up to the next marker
+    if (!marker || marker_pos + 1 >= n) return 0;
+    const unsigned m = __ldg(p + marker_pos + 1);
+    if (m < 0xD0u || m > 0xD7u) return 0;
+    start(marker_pos + 2u);
+    return 1;
+  }
+  __device__ __forceinline__ unsigned end_pos() const { return marker ? marker_pos : raw_pos; }
 };
 __device__ __forceinline__ int jextend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
 __device__ __forceinline__ int clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : x; }
@@ -134,6 +175,7 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
   __shared__ __align__(16) short s_blk[64];
   __shared__ int s_val[64];
   __shared__ __align__(16) FrameDesc s_fd;
+  __shared__ __align__(16) unsigned char s_ring[kCleanRing];
   const int lane = threadIdx.x;
   {
     const unsigned* src = reinterpret_cast<const unsigned*>(fd + blockIdx.x);
@@ -151,8 +193,9 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
   __syncwarp();
   const unsigned char* d = in + f.src_off;
   unsigned char* pl = planes + (size_t)blockIdx.x * plane_stride;
-  DevBits br{d, f.n_bytes, f.scan_start, 0u, 0, false, 0u, 0u};
-  br.window(br.pos);
+  CleanBits br;
+  br.p = d; br.n = f.n_bytes; br.ring = s_ring; br.lane = lane;
+  br.start(f.scan_start);
   int dc_pred[3] = {0, 0, 0};
   int todo = f.restart ? (int)f.restart : 0x7fffffff;
   int rc = JST_OK;
@@ -173,12 +216,10 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
           dc_pred[k] += diff;
           if (lane == 0) s_blk[0] = (short)(dc_pred[k] * q[0]);
           for (int kk = 1; kk < 64;) {
-            if (br.cnt < 16) br.fill();
-            const int fa = ha.fast_ac[br.buf >> (32 - kFastBits)];
+            const int fa = ha.fast_ac[br.peek() >> (32 - kFastBits)];
             if (fa) {                                             // short code + small coefficient in one lookup
               kk += (fa >> 4) & 15;
-              const int used = fa & 15;
-              br.buf <<= used; br.cnt -= used;
+              br.consume((unsigned)(fa & 15));
               const int z = c_zig[kk++];
               if (lane == 0) s_blk[z] = (short)((fa >> 8) * q[z]);
               continue;
@@ -216,24 +257,16 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
       if (rc != JST_OK) break;
       // ---- restart interval (jpeg.cpp: handle_restart; stb_image.h:2451-2470)
       if (--todo <= 0) {
-        br.reset();
-        unsigned qpos = br.pos;
-        bool bad = false;
-        while (qpos + 1 < f.n_bytes) {
-          const unsigned a = __ldg(d + qpos), b2 = __ldg(d + qpos + 1);
-          if (a == 0xFFu && b2 >= 0xD0u && b2 <= 0xD7u) break;
-          if (a == 0xFFu && b2 != 0 && b2 != 0xFFu) { bad = true; break; }
-          ++qpos;
+        if (!br.restart()) {                                       // no RSTn follows: the host decoder stops decoding here ("ended")
+          rc = (my == f.mcuy - 1 && mx == f.mcux - 1) ? JST_OK : JST_BAD_RESTART;   // unfinished planes are the host decoder's business
+          my = f.mcuy; break;
         }
-        if (bad || qpos + 1 >= f.n_bytes) { rc = (my == f.mcuy - 1 && mx == f.mcux - 1) ? JST_OK : JST_BAD_RESTART; my = f.mcuy; break; }   // the host stops decoding here too ("ended")
-        br.pos = qpos + 2;
-        br.window(br.pos);
         dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
         todo = f.restart ? (int)f.restart : 0x7fffffff;
       }
     }
   }
-  if (lane == 0) { status[blockIdx.x] = rc; end_pos[blockIdx.x] = br.pos; }
+  if (lane == 0) { status[blockIdx.x] = rc; end_pos[blockIdx.x] = br.end_pos(); }
 }
 
 // ---- up-sampling + colour conversion, one thread per output pixel -----------------------------------------------------------------
@@ -397,6 +430,8 @@ bool tail_is_plain(const uint8_t* d, size_t n, size_t pos) {
 constexpr size_t kJSlice = size_t(64) << 20;
 struct JpegStage {
   uint8_t* h[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t tk[3] = {nullptr, nullptr, nullptr};   // timing events: before the entropy kernel, between, after the colour kernel
+  double last_host_s = 0, last_entropy_ms = 0, last_color_ms = 0;
   uint8_t* d_in = nullptr; size_t in_cap = 0;
   uint8_t* d_planes = nullptr; size_t planes_cap = 0;
   FrameDesc* d_fd = nullptr; int* d_status = nullptr; unsigned* d_end = nullptr; size_t ncap = 0;
@@ -405,6 +440,7 @@ struct JpegStage {
     for (int i = 0; i < 2; ++i) if (!h[i]) {
       if (cudaHostAlloc((void**)&h[i], kJSlice, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
     }
+    for (int i = 0; i < 3; ++i) if (!tk[i] && cudaEventCreate(&tk[i]) != cudaSuccess) { cudaGetLastError(); return false; }
     auto grow = [](void** p, size_t* cap, size_t want) {
       if (want <= *cap) return true;
       cudaFree(*p); *p = nullptr; *cap = 0;
@@ -445,6 +481,7 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
   if (!src || !src_bytes || !d_out || !width || !height) return scn::fail(SCN_ERR_ARG, "null argument");
   if (!d_lut) out_px = width * height;
   cudaStream_t st = (cudaStream_t)stream;
+  const double t_call = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   // 1. parse (a few host threads), collect distinct table sets
   std::vector<Parsed> P(n); std::vector<TableSet> ts_all(n);
   {
@@ -500,8 +537,11 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
   }
   // 3. decode
   std::vector<int> status(n, JST_UNSUPPORTED); std::vector<unsigned> endp(n, 0);
+  const double t_packed = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   if (e == cudaSuccess) {
+    cudaEventRecord(g.tk[0], st);
     k_jpeg_entropy_idct<<<n, 32, 0, st>>>(g.d_in, g.d_fd, g.d_sets, g.d_planes, plane_stride, g.d_status, g.d_end);
+    cudaEventRecord(g.tk[1], st);
     e = cudaMemcpyAsync(status.data(), g.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(endp.data(), g.d_end, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
@@ -518,7 +558,13 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
   }
   if (e == cudaSuccess) {
     k_jpeg_color<<<dim3((out_px + 255) / 256, n), 256, 0, st>>>(g.d_fd, g.d_planes, plane_stride, g.d_status, d_lut, out_px, (unsigned char*)d_out);
+    cudaEventRecord(g.tk[2], st);
     e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    float ms = 0;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g.last_entropy_ms = ms;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[1], g.tk[2]) == cudaSuccess) g.last_color_ms = ms;
+    g.last_host_s = t_packed - t_call;
   }
   if (e != cudaSuccess) return scn::fail(SCN_ERR_CUDA, "scn_jpeg_decode_batch_device: %s", cudaGetErrorString(e));
   if (n_on_device) *n_on_device = n - (uint32_t)redo.size();
@@ -541,6 +587,15 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
     }
   }
   SCN_CUDA_TRY(cudaStreamSynchronize(st));
+  return SCN_OK;
+}
+
+// timings of the last scn_jpeg_decode_batch_device call of this thread: host parse + pack + upload issue (s), entropy+IDCT kernel
+// and colour kernel (ms, CUDA events)
+int scn_jpeg_last_timings(double* host_s, double* entropy_ms, double* color_ms) {
+  if (host_s) *host_s = g_jstage.last_host_s;
+  if (entropy_ms) *entropy_ms = g_jstage.last_entropy_ms;
+  if (color_ms) *color_ms = g_jstage.last_color_ms;
   return SCN_OK;
 }
 

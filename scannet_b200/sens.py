@@ -155,3 +155,17 @@ def inflate_host(data: bytes, cap: int) -> bytes:
     out = np.zeros(max(cap, 1), np.uint8); n = C.c_size_t()
     check(_L().scn_inflate_host(data, C.c_size_t(len(data)), out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n)))
     return out[: n.value].tobytes()
+
+
+def inflate_last_timings():
+    """(pack_s, kernel_ms, ring_window, n_streams) of this thread's last inflate_batch_device / decode_depth_device"""
+    a = C.c_double(); b = C.c_double(); r = C.c_int(); n = C.c_uint32()
+    _L().scn_inflate_last_timings(C.byref(a), C.byref(b), C.byref(r), C.byref(n))
+    return a.value, b.value, bool(r.value), n.value
+
+
+def jpeg_last_timings():
+    """(host_s, entropy_idct_kernel_ms, colour_kernel_ms) of this thread's last jpeg_decode_batch_device / decode_color_device"""
+    a = C.c_double(); b = C.c_double(); c = C.c_double()
+    _L().scn_jpeg_last_timings(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value

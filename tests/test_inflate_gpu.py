@@ -83,3 +83,20 @@ def test_truncated_dynamic_block_is_an_error_on_the_device_too(built):
     out = torch.zeros((2, len(raw)), dtype=torch.uint8, device="cuda")
     with pytest.raises(ScnError, match="truncated"):
         sens.inflate_batch_device([zlib.compress(raw, 6), bad], len(raw), out.data_ptr())
+
+
+@pytest.mark.parametrize("window", ["ring", "hbm"])
+def test_both_window_placements_give_the_same_bytes(built, window, monkeypatch):
+    """the shared-memory-ring kernel (small launches) and the HBM-window kernel (large launches) are the same decoder with the
+    deflate window in two places; SCN_INFLATE_WINDOW forces one"""
+    monkeypatch.setenv("SCN_INFLATE_WINDOW", window)
+    rng = np.random.default_rng(11)
+    base = (rng.integers(400, 5000, (480, 640)) // 2 * 2).astype("<u2"); base[100:140] = 0
+    frames = [np.roll(base, 13 * i, axis=1).copy() for i in range(48)]
+    encs = list(encoders().values())
+    streams = [encs[i % len(encs)](fr.tobytes()) for i, fr in enumerate(frames)]
+    out = torch.zeros((len(frames), 480, 640), dtype=torch.int16, device="cuda")
+    sens.inflate_batch_device(streams, 640 * 480 * 2, out.data_ptr())
+    got = out.cpu().numpy().view(np.uint16)
+    assert all((got[i] == frames[i]).all() for i in range(len(frames)))
+    assert sens.inflate_last_timings()[2] == (window == "ring")
