@@ -323,6 +323,8 @@ typedef struct scn_fuse_report {
   double   fuse_s;                 /* first frame in -> last frame integrated, decode included */
   double   decode_wait_s;          /* of which the integrator waited for the decoders */
   double   depth_decode_s, color_decode_s;   /* busy time of the two decoder threads (overlaps fuse_s) */
+  double   integrate_s;            /* integrator: submit + wait for the GPU, all chunks */
+  double   setup_s;                /* open + parse the file, create the volume, allocate the staging buffers */
   double   mc_s, ply_s, total_s;   /* marching cubes, PLY write, everything incl. opening the file */
 } scn_fuse_report_t;
 int  scn_fuse_scene(const char* sens_path, const char* out_ply /* NULL: no mesh */, const scn_tsdf_params* params, int device,

@@ -138,6 +138,7 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
                                                                                       : "GPU inflate (depth) + GPU JPEG (colour), compressed payloads uploaded");
   rep.gpu_decode = gpu_decode ? 1 : 0;
   const double t0 = now_s();
+  rep.setup_s = t0 - t_begin;
   int rc = 0; std::string err;
   auto fail_here = [&](const char* what) { if (!rc) { rc = 1; err = what && *what ? what : scn_last_error(); } };
   if (gpu_decode) {
@@ -240,8 +241,10 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
       rep.decode_wait_s += now_s() - tw0;
       const ChunkPlan& pl = plan[c];
       if (!pl.frames.empty()) {
+        const double ti0 = now_s();
         if (scn_tsdf_integrate_device(vol, (uint32_t)pl.frames.size(), d_depth[c & 1], use_color ? d_rgb[c & 1] : nullptr, pl.poses.data(), in.depth_intrinsic)) { fail_here(nullptr); break; }
         if (scn_tsdf_sync(vol)) { fail_here(nullptr); break; }                          // the buffers of this chunk may be overwritten now
+        rep.integrate_s += now_s() - ti0;
       }
       { std::lock_guard<std::mutex> l(m); consumed = c + 1; }
       cv.notify_all();

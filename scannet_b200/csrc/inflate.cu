@@ -453,7 +453,10 @@ struct InflateStage {
     return true;
   }
 };
-thread_local InflateStage g_stage;
+// released when the calling thread ends (the scene driver decodes on short-lived threads)
+struct InflateStageHolder { InflateStage s; ~InflateStageHolder() { s.release(); } };
+thread_local InflateStageHolder g_stage_holder;
+#define g_stage (g_stage_holder.s)
 
 }  // namespace
 
@@ -513,7 +516,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   // HBM (matches read the output back through L2): 32 streams per SM.  Up to about two waves of ring streams the ring wins.
   static const int n_sm = []() { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
   const char* wenv = getenv("SCN_INFLATE_WINDOW");
-  const bool use_ring = wenv ? !strcmp(wenv, "ring") : n <= (uint32_t)(10 * n_sm);
+  const bool use_ring = wenv ? !strcmp(wenv, "ring") : n <= (uint32_t)(5 * n_sm);      // measured: 42 ms per wave of 740 (ring) vs 52-57 ms for up to ~1500 streams (HBM window)
   if (e == cudaSuccess) {
     cudaEventRecord(g.tk[0], st);
     if (use_ring) k_inflate<true><<<n, 32, sizeof(InflateScratchDev), st>>>(g.d, g.d_off, (uint8_t*)d_out, (size_t)frame_bytes, (size_t)frame_bytes, n, g.d_status, g.d_prod);

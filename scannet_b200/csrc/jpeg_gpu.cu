@@ -461,7 +461,17 @@ struct JpegStage {
     return true;
   }
 };
-thread_local JpegStage g_jstage;
+// released when the calling thread ends (the scene driver decodes on short-lived threads)
+struct JpegStageHolder {
+  JpegStage s;
+  ~JpegStageHolder() {
+    for (int i = 0; i < 2; ++i) { if (s.h[i]) cudaFreeHost(s.h[i]); if (s.ev[i]) cudaEventDestroy(s.ev[i]); }
+    for (int i = 0; i < 3; ++i) if (s.tk[i]) cudaEventDestroy(s.tk[i]);
+    cudaFree(s.d_in); cudaFree(s.d_planes); cudaFree(s.d_fd); cudaFree(s.d_status); cudaFree(s.d_end); cudaFree(s.d_sets);
+  }
+};
+thread_local JpegStageHolder g_jstage_holder;
+#define g_jstage (g_jstage_holder.s)
 
 }  // namespace
 

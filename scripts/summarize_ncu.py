@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns gpurun_out/*.ncu-rep + launches_*.csv into the small text summaries committed under profiles/.
-Usage: python scripts/summarize_ncu.py <tag>      (reads gpurun_out/, writes profiles/<tag>_*.md)"""
+Usage: python scripts/summarize_ncu.py <tag> [batch_frames=32]     (reads gpurun_out/, writes profiles/<tag>_*.md and profiles/latest_traffic.json)"""
 import csv
 import io
 import os
@@ -123,7 +123,7 @@ def main():
         kint = next((k for k in tr if k.startswith("k_integrate")), None)
         with open(os.path.join(p, "latest_traffic.json"), "w") as fh:
             json.dump({"tag": tag, "source": "ncu --set full --clock-control none, bench.py --steps 2 --warmup 1 --scene-frames 96 --frames-per-step 96 (default batch)",
-                       "batch": 16, "integrate_kernel": kint,
+                       "batch": int(sys.argv[2]) if len(sys.argv) > 2 else 32, "integrate_kernel": kint,
                        "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in tr.items()},
                        "issue_active": {k: sum(v) / len(v) for k, v in issue.items()},
                        "warp_inst_per_launch": {k: sum(v) / len(v) for k, v in inst.items()},
