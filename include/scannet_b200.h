@@ -324,6 +324,8 @@ typedef struct scn_fuse_report {
   double   decode_wait_s;          /* of which the integrator waited for the decoders */
   double   depth_decode_s, color_decode_s;   /* busy time of the two decoder threads (overlaps fuse_s) */
   double   integrate_s;            /* integrator: submit + wait for the GPU, all chunks */
+  double   depth_pack_s, depth_kernel_s;     /* of depth_decode_s: host packing + upload issue, inflate kernel (CUDA events) */
+  double   color_host_s, color_entropy_s, color_convert_s;   /* of color_decode_s: host parse + pack, Huffman+IDCT kernel, colour kernel */
   double   setup_s;                /* open + parse the file, create the volume, allocate the staging buffers */
   double   mc_s, ply_s, total_s;   /* marching cubes, PLY write, everything incl. opening the file */
 } scn_fuse_report_t;

@@ -212,10 +212,13 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
           } else if (is_color) {
             uint32_t k = 0;
             r = scn_jpeg_decode_batch_device(src.data(), len.data(), n, in.color_width, in.color_height, d_lut, (uint32_t)px, d_rgb[c & 1], st_c, &k);
-            if (!r) { std::lock_guard<std::mutex> l(m); rep.color_frames_on_device += k; rep.color_decode_s += now_s() - td0; }
+            double hs = 0, em = 0, cm = 0; scn_jpeg_last_timings(&hs, &em, &cm);
+            if (!r) { std::lock_guard<std::mutex> l(m); rep.color_frames_on_device += k; rep.color_decode_s += now_s() - td0;
+                      rep.color_host_s += hs; rep.color_entropy_s += em * 1e-3; rep.color_convert_s += cm * 1e-3; }
           } else if (in.depth_compression == 1) {
             r = scn_inflate_batch_device(src.data(), len.data(), n, (uint64_t)px * 2, d_depth[c & 1], st_d);
-            if (!r) { std::lock_guard<std::mutex> l(m); rep.depth_decode_s += now_s() - td0; }
+            double ps = 0, km = 0; scn_inflate_last_timings(&ps, &km, nullptr, nullptr);
+            if (!r) { std::lock_guard<std::mutex> l(m); rep.depth_decode_s += now_s() - td0; rep.depth_pack_s += ps; rep.depth_kernel_s += km * 1e-3; }
           } else {
             for (uint32_t i = 0; i < n && !r; ++i) {
               if (len[i] < px * 2) { r = scn::fail(SCN_ERR_FORMAT, "frame %llu: invalid data", (unsigned long long)pl.frames[i]); break; }

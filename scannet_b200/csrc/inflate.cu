@@ -33,11 +33,15 @@ struct HuffTab {                     // canonical Huffman code, lengths 1..15
   uint16_t first[16];                // first code of each length
   uint16_t offs[16];                 // index of that code's symbol in sym[]
   uint16_t sym[288];
-  uint32_t fast[512];                // 9-bit lookahead (stream bit order) -> packed entry (below); 0 = code longer than 9 bits
+  uint32_t fast[1024];               // 10-bit lookahead (stream bit order) -> packed entry (below); kLongCode = code longer than 10 bits
 };
 // Packed table entry: everything the main loop needs from one shared-memory load.
-//   bits 0-3 code length, 4-7 number of extra bits, 8-9 kind, 16-31 value (literal byte / length base / distance base / symbol)
+//   bits 0-3 code length, 4-7 number of extra bits, 8-9 kind, 10-14 code length + extra bits, 16-31 value (literal byte /
+//   length base / distance base / symbol)
 enum { K_LIT = 0, K_BASE = 1, K_EOB = 2, K_BAD = 3 };
+constexpr int kFastBits = 10;
+constexpr uint32_t kFastSize = 1u << kFastBits;
+constexpr uint32_t kLongCode = K_BAD << 8;           // kind "bad" with code length 0: the code is longer than the lookahead
 enum { M_PLAIN = 0, M_LITLEN = 1, M_DIST = 2 };     // what the symbols of a table mean
 struct InflateScratch { HuffTab lit, dist; uint8_t lens[320]; };
 constexpr uint32_t kWin = 32768;                                   // deflate window = the shared-memory ring of the device decoder
@@ -123,17 +127,17 @@ SCN_HD void lanes_sync() {
 }
 
 SCN_HD uint32_t make_entry(int mode, unsigned sym, unsigned len) {
-  if (mode == M_PLAIN) return len | (K_LIT << 8) | (sym << 16);
+  if (mode == M_PLAIN) return len | (K_LIT << 8) | (len << 10) | (sym << 16);
   if (mode == M_LITLEN) {
-    if (sym < 256u) return len | (K_LIT << 8) | (sym << 16);
-    if (sym == 256u) return len | (K_EOB << 8);
-    if (sym > 285u) return len | (K_BAD << 8);
+    if (sym < 256u) return len | (K_LIT << 8) | (len << 10) | (sym << 16);
+    if (sym == 256u) return len | (K_EOB << 8) | (len << 10);
+    if (sym > 285u) return len | (K_BAD << 8) | (len << 10);
     const unsigned lc = len_code(sym - 257u);
-    return len | ((lc & 15u) << 4) | (K_BASE << 8) | ((lc >> 4) << 16);
+    return len | ((lc & 15u) << 4) | (K_BASE << 8) | ((len + (lc & 15u)) << 10) | ((lc >> 4) << 16);
   }
-  if (sym > 29u) return len | (K_BAD << 8);
+  if (sym > 29u) return len | (K_BAD << 8) | (len << 10);
   const unsigned dc = dist_code(sym);
-  return len | ((dc & 15u) << 4) | (K_BASE << 8) | ((dc >> 4) << 16);
+  return len | ((dc & 15u) << 4) | (K_BASE << 8) | ((len + (dc & 15u)) << 10) | ((dc >> 4) << 16);
 }
 
 // canonical code from code lengths + the 9-bit lookahead table (filled by all lanes together); returns false for an
@@ -154,7 +158,7 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mod
     code = (code + cnt[l - 1]) << 1;
     h.count[l] = cnt[l]; h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += cnt[l];
   }
-  for (int j = lane; j < 512; j += LANES) h.fast[j] = 0;
+  for (int j = lane; j < (int)kFastSize; j += LANES) h.fast[j] = kLongCode;
   lanes_sync<LANES>();
   uint16_t nexti[16], nextc[16];
   { unsigned c2 = 0, o2 = 0; for (int l = 1; l < 16; ++l) { c2 = (c2 + cnt[l - 1]) << 1; nextc[l] = (uint16_t)c2; nexti[l] = (uint16_t)o2; o2 += cnt[l]; } }
@@ -163,10 +167,10 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mod
     if (!l) continue;
     const unsigned c = nextc[l]++;
     h.sym[nexti[l]++] = (uint16_t)i;
-    if (l <= 9) {
+    if (l <= kFastBits) {
       const unsigned r = rev_bits(c, l);
       const uint32_t e = make_entry(mode, (unsigned)i, (unsigned)l);
-      for (unsigned j = r + ((unsigned)lane << l); j < 512u; j += (unsigned)LANES << l) h.fast[j] = e;
+      for (unsigned j = r + ((unsigned)lane << l); j < kFastSize; j += (unsigned)LANES << l) h.fast[j] = e;
     }
   }
   return true;
@@ -174,10 +178,10 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mod
 // decode one symbol into a packed entry whose code bits are already consumed (caller guarantees >= 15 bits in the buffer:
 // bi_refill leaves > 32); an invalid code gives kind K_BAD
 SCN_HD uint32_t huff_decode(BitIn& b, const HuffTab& h, int mode) {
-  const uint32_t e = h.fast[bi_peek(b, 9)];
-  if (e) { bi_drop(b, (int)(e & 15u)); return e; }
+  const uint32_t e = h.fast[bi_peek(b, kFastBits)];
+  if (e != kLongCode) { bi_drop(b, (int)(e & 15u)); return e; }
   const unsigned r = rev_bits(bi_peek(b, 15), 15);
-  for (int l = 10; l < 16; ++l) {
+  for (int l = kFastBits + 1; l < 16; ++l) {
     const unsigned c = (r >> (15 - l)) - h.first[l];
     if (c < h.count[l]) { bi_drop(b, l); return make_entry(mode, h.sym[h.offs[l] + c], (unsigned)l); }
   }
@@ -207,61 +211,103 @@ struct FastBits {
   }
   __device__ __forceinline__ uint32_t bitpos() const { return (wi << 5) + off; }
 };
-__device__ __forceinline__ uint32_t long_code(const HuffTab& h, uint32_t win, int mode) {     // codes of 10..15 bits
+// shared memory through 32-bit addresses (the generic-pointer form made ptxas re-derive the shared window per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t long_code(const HuffTab& h, uint32_t win, int mode) {     // codes of 11..15 bits
   const unsigned r = __brev(win & 0x7FFFu) >> 17;
-  for (int l = 10; l < 16; ++l) {
+  for (int l = kFastBits + 1; l < 16; ++l) {
     const unsigned c = (r >> (15 - l)) - h.first[l];
     if (c < h.count[l]) return make_entry(mode, h.sym[h.offs[l] + c], (unsigned)l);
   }
   return K_BAD << 8;
 }
 // symbols of one Huffman block until its end-of-block code.  Returns INF_OK at EOB, INF_OUT_FULL when the frame is complete.
-// RING: the window is the shared-memory ring (+ a copy of every byte streamed to HBM); !RING: the window is the output in HBM
+// RING: the window is the shared-memory ring (+ a copy of every byte streamed to HBM); !RING: the window is the output in HBM.
+// ~20 instructions per literal, ~50 per match: one table load per code, the kind tested on single bits in the order
+// literal / match / rest, code length + extra bits pre-added in the entry, shared memory addressed with 32-bit registers.
+// A stream that ends early decodes the zero padding; every exit reports INF_TRUNCATED when the reader is past the end.
 template <bool RING>
-__device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScratch& S, uint8_t* ring, uint8_t* out, uint32_t& o, uint32_t cap,
+__device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScratch& S, uint8_t* ring, uint8_t* out_in, uint32_t& o_io, uint32_t cap_in,
                                                   int lane, uint32_t nbits) {
-  uint8_t* const wbase = RING ? ring : out;
-  const uint32_t wmask = RING ? kWin - 1u : 0xFFFFFFFFu;
+  // A zero ptxas cannot see through: without it the shared-memory window base (S2UR SR_CgaCtaId + ULEA) and the stream's
+  // output pointer (two IMADs of blockIdx and the stride) are re-derived for every symbol instead of being kept in registers.
+  __shared__ volatile uint32_t s_zero;
+  s_zero = 0u;
+  __syncwarp();
+  const uint32_t z = s_zero;
+  const uint32_t s_lit = (uint32_t)__cvta_generic_to_shared(S.lit.fast) + z, s_dist = (uint32_t)__cvta_generic_to_shared(S.dist.fast) + z;
+  const uint32_t s_ring = (RING ? (uint32_t)__cvta_generic_to_shared(ring) : 0u) + z;
+  uint8_t* const out = out_in + z;
+  const uint32_t cap = cap_in + z;
+  uint32_t o = o_io;
+  int rc;
   for (;;) {
     uint32_t win = fb.peek();
-    uint32_t e = S.lit.fast[win & 511u];
-    if (!e) e = long_code(S.lit, win, M_LITLEN);
-    const uint32_t clen = e & 15u, kind = (e >> 8) & 3u;
-    if (kind == K_LIT) {
-      if (o >= cap) return fb.bitpos() > nbits ? INF_TRUNCATED : INF_OUT_FULL;                // (zero padding past a truncated stream decodes as literals)
-      fb.drop(clen);
-      if (lane == 0) { const uint8_t v = (uint8_t)(e >> 16); if (RING) ring[o & (kWin - 1u)] = v; out[o] = v; }
+    uint32_t e = lds32(s_lit + ((win << 2) & ((kFastSize - 1u) << 2)));
+  dispatch:
+    if ((e & 0x300u) == 0u) {                                                                    // literal (every lane stores the same byte to the same place)
+      if (o >= cap) { rc = INF_OUT_FULL; break; }
+      fb.drop(e & 15u);
+      const uint32_t v = e >> 16;
+      if (RING) sts8(s_ring + (o & (kWin - 1u)), v);
+      out[o] = (uint8_t)v;
       ++o;
       continue;
     }
-    if (kind == K_EOB) { fb.drop(clen); return INF_OK; }
-    if (kind == K_BAD) return INF_BAD_CODE;
-    const uint32_t xb = (e >> 4) & 15u;
-    uint32_t len = (e >> 16) + ((win >> clen) & ((1u << xb) - 1u));                            // code + extra bits <= 20
-    fb.drop(clen + xb);
+    if ((e & 0x200u) != 0u) {                                                                    // end of block, bad code, or a code longer than the lookahead
+      if (e == kLongCode) { e = long_code(S.lit, win, M_LITLEN); if (e != kLongCode) goto dispatch; }
+      if (((e >> 8) & 3u) == K_EOB) { fb.drop(e & 15u); rc = INF_OK; break; }
+      rc = INF_BAD_CODE; break;
+    }
+    // match: length = base + extra bits, i.e. bits [code length, code length + extra) of the window
+    uint32_t len = (e >> 16) + ((win & ~(0xFFFFFFFFu << ((e >> 10) & 31u))) >> (e & 15u));        // code + extra bits <= 20
+    fb.drop((e >> 10) & 31u);
     win = fb.peek();
-    uint32_t d = S.dist.fast[win & 511u];
-    if (!d) d = long_code(S.dist, win, M_DIST);
-    if (((d >> 8) & 3u) != K_BASE) return INF_BAD_CODE;
-    const uint32_t dl = d & 15u, dxb = (d >> 4) & 15u;                                          // code + extra bits <= 28
-    const uint32_t dist = (d >> 16) + ((win >> dl) & ((1u << dxb) - 1u));
-    fb.drop(dl + dxb);
-    if (fb.bitpos() > nbits) return INF_TRUNCATED;
-    if (dist > o) return INF_BAD_DIST;
+    uint32_t d = lds32(s_dist + ((win << 2) & ((kFastSize - 1u) << 2)));
+    if ((d & 0x300u) != (K_BASE << 8)) {
+      if (d == kLongCode) d = long_code(S.dist, win, M_DIST);
+      if ((d & 0x300u) != (K_BASE << 8)) { rc = INF_BAD_CODE; break; }
+    }
+    const uint32_t dist = (d >> 16) + ((win & ~(0xFFFFFFFFu << ((d >> 10) & 31u))) >> (d & 15u));   // code + extra bits <= 28
+    fb.drop((d >> 10) & 31u);
+    if (dist > o) { rc = INF_BAD_DIST; break; }
     const bool full = o + len > cap;
     if (full) len = cap - o;                                                                     // the caller's frame is complete: write what fits and stop
     __syncwarp();                                                                                // earlier literals / matches are visible to every lane
     const uint32_t so = o - dist;
     if (dist >= len) {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + i) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
-    } else if ((dist & (dist - 1u)) == 0u) {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + (i & (dist - 1u))) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+      uint32_t i = (uint32_t)lane;
+      if (i < len) {
+        uint32_t v;
+        if (RING) { v = lds8(s_ring + ((so + i) & (kWin - 1u))); sts8(s_ring + ((o + i) & (kWin - 1u)), v); } else v = out[so + i];
+        out[o + i] = (uint8_t)v;
+      }
+      if (len > 32u) {
+#pragma unroll 1
+        for (i += 32u; i < len; i += 32u) {
+          uint32_t v;
+          if (RING) { v = lds8(s_ring + ((so + i) & (kWin - 1u))); sts8(s_ring + ((o + i) & (kWin - 1u)), v); } else v = out[so + i];
+          out[o + i] = (uint8_t)v;
+        }
+      }
     } else {
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) { const uint8_t v = wbase[(so + i % dist) & wmask]; if (RING) ring[(o + i) & (kWin - 1u)] = v; out[o + i] = v; }
+#pragma unroll 1
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
+        const uint32_t k = (dist & (dist - 1u)) == 0u ? (i & (dist - 1u)) : i % dist;
+        uint32_t v;
+        if (RING) { v = lds8(s_ring + ((so + k) & (kWin - 1u))); sts8(s_ring + ((o + i) & (kWin - 1u)), v); } else v = out[so + k];
+        out[o + i] = (uint8_t)v;
+      }
     }
     o += len;
-    if (full) return INF_OUT_FULL;
+    if (full) { rc = INF_OUT_FULL; break; }
   }
+  o_io = o;
+  __syncwarp();
+  if (fb.bitpos() > nbits) rc = INF_TRUNCATED;
+  return rc;
 }
 #endif
 
@@ -371,11 +417,11 @@ SCN_HD int inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
           continue;
         }
         if (kind == K_EOB) break;
-        if (kind == K_BAD) return INF_BAD_CODE;
+        if (kind == K_BAD) return bi_overrun(b) ? INF_TRUNCATED : INF_BAD_CODE;
         unsigned len = (e >> 16) + bi_get(b, (int)((e >> 4) & 15u));
         bi_refill(b);
         const uint32_t d = huff_decode(b, S.dist, M_DIST);
-        if (((d >> 8) & 3u) != K_BASE) return INF_BAD_CODE;
+        if (((d >> 8) & 3u) != K_BASE) return bi_overrun(b) ? INF_TRUNCATED : INF_BAD_CODE;
         const unsigned dist = (d >> 16) + bi_get(b, (int)((d >> 4) & 15u));
         if (bi_overrun(b)) return INF_TRUNCATED;
         if (dist > o) return INF_BAD_DIST;
