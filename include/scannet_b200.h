@@ -34,6 +34,9 @@ int  scn_version(void);
 int  scn_device_count(void);
 /* Creates the CUDA context now (≈0.3 s in a cold process); safe to call from a helper thread while input files are read. */
 int  scn_cuda_warmup(void);
+/* The batch decoders (scn_inflate_batch_device, scn_jpeg_decode_batch_device, scn_fuse_*) keep their pinned upload slices and
+ * device scratch buffers in a per-device pool for the life of the process; this frees the idle ones of the current device. */
+int  scn_release_cached_staging(void);
 /* Pinned host memory for frame staging (cudaHostAlloc); integrate calls detect it and skip the bounce copy. */
 void* scn_host_alloc(size_t bytes);
 void  scn_host_free(void* p);

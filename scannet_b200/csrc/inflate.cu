@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "scn_common.h"
+#include "stage_pool.h"
 
 #define SCN_HD __host__ __device__ __forceinline__
 
@@ -470,9 +471,9 @@ const char* inf_msg(int rc) {
 // bounded and reused), a device buffer for the packed streams, per-stream offsets / status / produced counts
 constexpr size_t kSlice = size_t(64) << 20;
 struct InflateStage {
+  int device = 0;
   uint8_t* h[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t tk[2] = {nullptr, nullptr};            // timing events around the kernel
-  double last_pack_s = 0, last_kernel_ms = 0; int last_ring = 0; unsigned last_n = 0;
   uint8_t* d = nullptr; size_t cap = 0;
   unsigned long long* d_off = nullptr; int* d_status = nullptr; unsigned long long* d_prod = nullptr; size_t ncap = 0;
   void release() {
@@ -499,10 +500,9 @@ struct InflateStage {
     return true;
   }
 };
-// released when the calling thread ends (the scene driver decodes on short-lived threads)
-struct InflateStageHolder { InflateStage s; ~InflateStageHolder() { s.release(); } };
-thread_local InflateStageHolder g_stage_holder;
-#define g_stage (g_stage_holder.s)
+scn::StagePool<InflateStage>& inflate_pool() { static auto* p = new scn::StagePool<InflateStage>(); return *p; }
+struct InflateTimings { double pack_s = 0, kernel_ms = 0; int ring = 0; unsigned n = 0; };
+thread_local InflateTimings g_last;
 
 }  // namespace
 
@@ -534,7 +534,8 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
     off[i] = tot; tot += ((size_t)src_bytes[i] + 15) & ~size_t(15);
   }
   off[n] = tot;
-  InflateStage& g = g_stage;
+  scn::StagePool<InflateStage>::Lease lease(inflate_pool());
+  InflateStage& g = *lease;
   if (!g.ensure(tot + 16, n)) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: allocation of %zu staging bytes failed", tot);
   cudaError_t e = cudaMemcpyAsync(g.d_off, off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st);
   const unsigned nt = std::max(1u, std::min(24u, std::thread::hardware_concurrency()));     // packing is a 2-3 GB memcpy per scan: spread it
@@ -574,7 +575,7 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return scn::fail(SCN_ERR_CUDA, "scn_inflate_batch_device: %s", cudaGetErrorString(e));
-  { float ms = 0; if (cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g.last_kernel_ms = ms; g.last_pack_s = t_packed - t_call; g.last_ring = use_ring; g.last_n = n; }
+  { float ms = 0; if (cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g_last.kernel_ms = ms; g_last.pack_s = t_packed - t_call; g_last.ring = use_ring; g_last.n = n; }
   for (uint32_t i = 0; i < n; ++i) {
     if (status[i] != INF_OK && status[i] != INF_OUT_FULL) return scn::fail(SCN_ERR_FORMAT, "frame %u: corrupt zlib depth stream (%s)", i, inf_msg(status[i]));
     if (prod[i] < frame_bytes) return scn::fail(SCN_ERR_FORMAT, "frame %u: depth stream holds %llu bytes, need %llu", i, prod[i], (unsigned long long)frame_bytes);
@@ -584,11 +585,13 @@ int scn_inflate_batch_device(const uint8_t* const* src, const uint64_t* src_byte
 
 // timings of the last scn_inflate_batch_device call of this thread: host packing + upload issue (s), inflate kernel (ms, CUDA
 // events), whether the shared-memory-window kernel ran, streams in the launch
+void scn_inflate_release_staging_() { inflate_pool().trim(); }
+
 int scn_inflate_last_timings(double* pack_s, double* kernel_ms, int* ring_window, uint32_t* n_streams) {
-  if (pack_s) *pack_s = g_stage.last_pack_s;
-  if (kernel_ms) *kernel_ms = g_stage.last_kernel_ms;
-  if (ring_window) *ring_window = g_stage.last_ring;
-  if (n_streams) *n_streams = g_stage.last_n;
+  if (pack_s) *pack_s = g_last.pack_s;
+  if (kernel_ms) *kernel_ms = g_last.kernel_ms;
+  if (ring_window) *ring_window = g_last.ring;
+  if (n_streams) *n_streams = g_last.n;
   return SCN_OK;
 }
 

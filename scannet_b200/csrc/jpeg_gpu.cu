@@ -25,6 +25,7 @@
 
 #include "jpeg_tables.h"
 #include "scn_common.h"
+#include "stage_pool.h"
 
 namespace scn { int jpeg_decode_rgb8(const uint8_t* d, size_t n, uint32_t want_w, uint32_t want_h, uint8_t* out); }
 
@@ -429,9 +430,9 @@ bool tail_is_plain(const uint8_t* d, size_t n, size_t pos) {
 
 constexpr size_t kJSlice = size_t(64) << 20;
 struct JpegStage {
+  int device = 0;
   uint8_t* h[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t tk[3] = {nullptr, nullptr, nullptr};   // timing events: before the entropy kernel, between, after the colour kernel
-  double last_host_s = 0, last_entropy_ms = 0, last_color_ms = 0;
   uint8_t* d_in = nullptr; size_t in_cap = 0;
   uint8_t* d_planes = nullptr; size_t planes_cap = 0;
   FrameDesc* d_fd = nullptr; int* d_status = nullptr; unsigned* d_end = nullptr; size_t ncap = 0;
@@ -460,18 +461,16 @@ struct JpegStage {
     sets_cap = sc / sizeof(TableSet);
     return true;
   }
-};
-// released when the calling thread ends (the scene driver decodes on short-lived threads)
-struct JpegStageHolder {
-  JpegStage s;
-  ~JpegStageHolder() {
-    for (int i = 0; i < 2; ++i) { if (s.h[i]) cudaFreeHost(s.h[i]); if (s.ev[i]) cudaEventDestroy(s.ev[i]); }
-    for (int i = 0; i < 3; ++i) if (s.tk[i]) cudaEventDestroy(s.tk[i]);
-    cudaFree(s.d_in); cudaFree(s.d_planes); cudaFree(s.d_fd); cudaFree(s.d_status); cudaFree(s.d_end); cudaFree(s.d_sets);
+  void release() {
+    for (int i = 0; i < 2; ++i) { if (h[i]) cudaFreeHost(h[i]); h[i] = nullptr; if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    for (int i = 0; i < 3; ++i) { if (tk[i]) cudaEventDestroy(tk[i]); tk[i] = nullptr; }
+    cudaFree(d_in); cudaFree(d_planes); cudaFree(d_fd); cudaFree(d_status); cudaFree(d_end); cudaFree(d_sets);
+    d_in = d_planes = nullptr; d_fd = nullptr; d_status = nullptr; d_end = nullptr; d_sets = nullptr; in_cap = planes_cap = ncap = sets_cap = 0;
   }
 };
-thread_local JpegStageHolder g_jstage_holder;
-#define g_jstage (g_jstage_holder.s)
+scn::StagePool<JpegStage>& jpeg_pool() { static auto* p = new scn::StagePool<JpegStage>(); return *p; }
+struct JpegTimings { double host_s = 0, entropy_ms = 0, color_ms = 0; };
+thread_local JpegTimings g_jlast;
 
 }  // namespace
 
@@ -517,7 +516,8 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
     plane_stride = std::max(plane_stride, pb);
   }
   off[n] = in_total;
-  JpegStage& g = g_jstage;
+  scn::StagePool<JpegStage>::Lease lease(jpeg_pool());
+  JpegStage& g = *lease;
   if (!g.ensure(in_total + 16, plane_stride * n + 16, n, std::max<size_t>(1, sets.size()))) return scn::fail(SCN_ERR_CUDA, "scn_jpeg_decode_batch_device: device staging allocation failed");
   std::vector<FrameDesc> fd(n);
   for (uint32_t i = 0; i < n; ++i) fd[i] = P[i].d;
@@ -572,9 +572,9 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     float ms = 0;
-    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g.last_entropy_ms = ms;
-    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[1], g.tk[2]) == cudaSuccess) g.last_color_ms = ms;
-    g.last_host_s = t_packed - t_call;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[0], g.tk[1]) == cudaSuccess) g_jlast.entropy_ms = ms;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, g.tk[1], g.tk[2]) == cudaSuccess) g_jlast.color_ms = ms;
+    g_jlast.host_s = t_packed - t_call;
   }
   if (e != cudaSuccess) return scn::fail(SCN_ERR_CUDA, "scn_jpeg_decode_batch_device: %s", cudaGetErrorString(e));
   if (n_on_device) *n_on_device = n - (uint32_t)redo.size();
@@ -602,10 +602,12 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
 
 // timings of the last scn_jpeg_decode_batch_device call of this thread: host parse + pack + upload issue (s), entropy+IDCT kernel
 // and colour kernel (ms, CUDA events)
+void scn_jpeg_release_staging_() { jpeg_pool().trim(); }
+
 int scn_jpeg_last_timings(double* host_s, double* entropy_ms, double* color_ms) {
-  if (host_s) *host_s = g_jstage.last_host_s;
-  if (entropy_ms) *entropy_ms = g_jstage.last_entropy_ms;
-  if (color_ms) *color_ms = g_jstage.last_color_ms;
+  if (host_s) *host_s = g_jlast.host_s;
+  if (entropy_ms) *entropy_ms = g_jlast.entropy_ms;
+  if (color_ms) *color_ms = g_jlast.color_ms;
   return SCN_OK;
 }
 
