@@ -8,9 +8,10 @@
 //           table set (a stream normally has one), pack the payloads into pinned slices and upload them;
 //   k_jpeg_entropy_idct   ONE WARP PER FRAME: the entropy-coded segment is a single bit-serial chain (there are no
 //           synchronisation points without restart markers), so all 32 lanes run the same bit reader and Huffman decoder
-//           redundantly (broadcast loads, no divergence); after each 8x8 block the warp does the IDCT cooperatively (8 lanes
-//           = 8 columns, then 8 rows) out of shared memory and stores the block into the component plane in HBM.  The
-//           parallelism is across frames: a scan is thousands of frames, 10.5 KB of tables per warp = 21 frames per SM;
+//           redundantly (broadcast loads, no divergence); after each MCU (up to 6 blocks) the warp does the IDCT of all its
+//           blocks at once out of shared memory - one lane per column, then one lane per row, 32 of the 48 columns / rows of
+//           a 4:2:0 MCU per step, bank-conflict-free through padding - and stores the rows into the component planes in
+//           HBM.  The parallelism is across frames: a scan is thousands of frames, ~14 KB of shared memory per warp;
 //   k_jpeg_color          fully parallel: chroma up-sampling + YCbCr->RGB per output pixel, either the whole frame (RGB8) or only
 //           the colour pixels the depth image needs (a depth-pixel -> colour-pixel map), so that a 1296x968 frame feeding a
 //           640x480 integration never materialises at full resolution.
@@ -62,6 +63,7 @@ __constant__ unsigned char c_zig[64 + 15] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11
 // one funnel shift per peek, one shared-memory load per 32 bits.  The first version (byte-wise refill with the FF test on
 // the dependent chain) cost ~600 cycles per symbol.
 constexpr unsigned kCleanRing = 1024;
+constexpr int kMaxMcuBlocks = 6;           // 4 luma (2x2) + 2 chroma: the largest MCU the device path accepts
 struct CleanBits {
   const unsigned char* p; unsigned n;       // raw stream
   unsigned char* ring;                      // shared memory, kCleanRing bytes, 4-byte aligned
@@ -173,8 +175,11 @@ __global__ void __launch_bounds__(32)
 k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __restrict__ fd, const TableSet* __restrict__ sets,
                     unsigned char* __restrict__ planes, size_t plane_stride, int* __restrict__ status, unsigned* __restrict__ end_pos) {
   __shared__ __align__(16) TableSet S;
-  __shared__ __align__(16) short s_blk[64];
-  __shared__ int s_val[64];
+  // padded so that the 32 lanes of an IDCT pass (4 blocks x 8 columns / rows) hit 32 different banks: coefficient blocks 72
+  // shorts apart, intermediate rows 9 ints apart
+  __shared__ __align__(16) short s_blk[kMaxMcuBlocks][72];
+  __shared__ int s_val[kMaxMcuBlocks][72];
+  __shared__ unsigned s_bk[kMaxMcuBlocks];               // block b of an MCU: component | row << 8 | column << 16
   __shared__ __align__(16) FrameDesc s_fd;
   __shared__ __align__(16) unsigned char s_ring[kCleanRing];
   const int lane = threadIdx.x;
@@ -191,78 +196,88 @@ k_jpeg_entropy_idct(const unsigned char* __restrict__ in, const FrameDesc* __res
     uint4* dst = reinterpret_cast<uint4*>(&S);
     for (int i = lane; i < (int)(sizeof(TableSet) / 16); i += 32) dst[i] = src[i];
   }
+  const int ncomp = f.ncomp;
+  int nb = 0;
+  for (int k = 0; k < ncomp; ++k) for (int by = 0; by < f.cv[k]; ++by) for (int bx = 0; bx < f.ch[k]; ++bx) { if (lane == 0 && nb < kMaxMcuBlocks) s_bk[nb] = (unsigned)k | ((unsigned)by << 8) | ((unsigned)bx << 16); ++nb; }
   __syncwarp();
+  if (nb > kMaxMcuBlocks) { if (lane == 0) { status[blockIdx.x] = JST_UNSUPPORTED; end_pos[blockIdx.x] = 0; } return; }   // (parse_frame only passes samplings with <= 6 blocks)
   const unsigned char* d = in + f.src_off;
   unsigned char* pl = planes + (size_t)blockIdx.x * plane_stride;
   CleanBits br;
   br.p = d; br.n = f.n_bytes; br.ring = s_ring; br.lane = lane;
   br.start(f.scan_start);
-  int dc_pred[3] = {0, 0, 0};
+  int dc0 = 0, dc1 = 0, dc2 = 0;                         // DC predictors (selects, not an indexed array: that lives in local memory)
   int todo = f.restart ? (int)f.restart : 0x7fffffff;
   int rc = JST_OK;
-  const int ncomp = f.ncomp;
   for (unsigned my = 0; my < f.mcuy && rc == JST_OK; ++my) {
     for (unsigned mx = 0; mx < f.mcux && rc == JST_OK; ++mx) {
+      // ---- entropy decode of the MCU's blocks (jpeg.cpp: decode_block; stb_image.h:1719-1770), every lane the same
+      for (int w = lane; w < nb * 36; w += 32) reinterpret_cast<unsigned*>(s_blk)[w] = 0u;
+      __syncwarp();
+      int b = 0;
       for (int k = 0; k < ncomp && rc == JST_OK; ++k) {
         const HuffTab& hd = S.dc[f.td[k]];
         const HuffTab& ha = S.ac[f.ta[k]];
         const unsigned char* q = S.quant[f.tq[k]];
-        for (int by = 0; by < f.cv[k] && rc == JST_OK; ++by) for (int bx = 0; bx < f.ch[k]; ++bx) {
-          // ---- entropy decode of one block (jpeg.cpp: decode_block; stb_image.h:1719-1770), every lane the same
-          reinterpret_cast<unsigned*>(s_blk)[lane] = 0u;
-          __syncwarp();
+        const int nbk = f.cv[k] * f.ch[k];
+        for (int j = 0; j < nbk; ++j, ++b) {
+          short* blk = s_blk[b];
           const int t = br.decode(hd);
           if (t < 0 || t > 16) { rc = JST_BAD_CODE; break; }
           const int diff = t ? jextend(br.get(t), t) : 0;
-          dc_pred[k] += diff;
-          if (lane == 0) s_blk[0] = (short)(dc_pred[k] * q[0]);
+          const int dc = (k == 0 ? dc0 : k == 1 ? dc1 : dc2) + diff;
+          if (k == 0) dc0 = dc; else if (k == 1) dc1 = dc; else dc2 = dc;
+          if (lane == 0) blk[0] = (short)(dc * q[0]);
           for (int kk = 1; kk < 64;) {
             const int fa = ha.fast_ac[br.peek() >> (32 - kFastBits)];
             if (fa) {                                             // short code + small coefficient in one lookup
               kk += (fa >> 4) & 15;
               br.consume((unsigned)(fa & 15));
               const int z = c_zig[kk++];
-              if (lane == 0) s_blk[z] = (short)((fa >> 8) * q[z]);
+              if (lane == 0) blk[z] = (short)((fa >> 8) * q[z]);
               continue;
             }
             const int rs = br.decode(ha);
             if (rs < 0) { rc = JST_BAD_CODE; break; }
             const int sz = rs & 15, r = rs >> 4;
             if (sz == 0) { if (rs != 0xF0) break; kk += 16; }
-            else { kk += r; const int z = c_zig[kk++]; const int v = jextend(br.get(sz), sz); if (lane == 0) s_blk[z] = (short)(v * q[z]); }
+            else { kk += r; const int z = c_zig[kk++]; const int v = jextend(br.get(sz), sz); if (lane == 0) blk[z] = (short)(v * q[z]); }
           }
           if (rc != JST_OK) break;
-          __syncwarp();
-          // ---- IDCT (jpeg.cpp: idct8x8_scalar; stb_image.h:1928-2027): 8 lanes = 8 columns, then 8 lanes = 8 rows
-          if (lane < 8) {
-            const short* c = s_blk + lane; int* v = s_val + lane;
-            IDCT_1D(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56])
-            x0 += 512; x1 += 512; x2 += 512; x3 += 512;
-            v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10; v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
-            v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10; v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
-          }
-          __syncwarp();
-          if (lane < 8) {
-            const int* v = s_val + 8 * lane;
-            IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
-            const int bias = 65536 + (128 << 17);
-            x0 += bias; x1 += bias; x2 += bias; x3 += bias;
-            const unsigned lo = (unsigned)clamp8((x0 + t3) >> 17) | ((unsigned)clamp8((x1 + t2) >> 17) << 8) | ((unsigned)clamp8((x2 + t1) >> 17) << 16) | ((unsigned)clamp8((x3 + t0) >> 17) << 24);
-            const unsigned hi = (unsigned)clamp8((x3 - t0) >> 17) | ((unsigned)clamp8((x2 - t1) >> 17) << 8) | ((unsigned)clamp8((x1 - t2) >> 17) << 16) | ((unsigned)clamp8((x0 - t3) >> 17) << 24);
-            const size_t px = (size_t)f.plane_off[k] + (size_t)((my * f.cv[k] + by) * 8 + lane) * f.w2[k] + (size_t)(mx * f.ch[k] + bx) * 8;
-            *reinterpret_cast<uint2*>(pl + px) = make_uint2(lo, hi);
-          }
-          __syncwarp();
         }
       }
-      if (rc != JST_OK) break;
+      if (rc != JST_OK) break;                                     // (the host decoder takes over a frame flagged here: its planes are not used)
+      __syncwarp();
+      // ---- IDCT of all blocks of the MCU (jpeg.cpp: idct8x8_scalar; stb_image.h:1928-2027): one lane = one column, then one row
+      for (int tsk = lane; tsk < nb * 8; tsk += 32) {
+        const short* c = s_blk[tsk >> 3] + (tsk & 7); int* v = s_val[tsk >> 3] + (tsk & 7);
+        IDCT_1D(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56])
+        x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+        v[0] = (x0 + t3) >> 10; v[63] = (x0 - t3) >> 10; v[9] = (x1 + t2) >> 10; v[54] = (x1 - t2) >> 10;
+        v[18] = (x2 + t1) >> 10; v[45] = (x2 - t1) >> 10; v[27] = (x3 + t0) >> 10; v[36] = (x3 - t0) >> 10;
+      }
+      __syncwarp();
+      for (int tsk = lane; tsk < nb * 8; tsk += 32) {
+        const int row = tsk & 7;
+        const int* v = s_val[tsk >> 3] + 9 * row;
+        IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
+        const int bias = 65536 + (128 << 17);
+        x0 += bias; x1 += bias; x2 += bias; x3 += bias;
+        const unsigned lo = (unsigned)clamp8((x0 + t3) >> 17) | ((unsigned)clamp8((x1 + t2) >> 17) << 8) | ((unsigned)clamp8((x2 + t1) >> 17) << 16) | ((unsigned)clamp8((x3 + t0) >> 17) << 24);
+        const unsigned hi = (unsigned)clamp8((x3 - t0) >> 17) | ((unsigned)clamp8((x2 - t1) >> 17) << 8) | ((unsigned)clamp8((x1 - t2) >> 17) << 16) | ((unsigned)clamp8((x0 - t3) >> 17) << 24);
+        const unsigned bk = s_bk[tsk >> 3];
+        const unsigned k = bk & 255u, by = (bk >> 8) & 255u, bx = bk >> 16;
+        const size_t px = (size_t)f.plane_off[k] + (size_t)((my * f.cv[k] + by) * 8 + row) * f.w2[k] + (size_t)(mx * f.ch[k] + bx) * 8;
+        *reinterpret_cast<uint2*>(pl + px) = make_uint2(lo, hi);
+      }
+      __syncwarp();
       // ---- restart interval (jpeg.cpp: handle_restart; stb_image.h:2451-2470)
       if (--todo <= 0) {
         if (!br.restart()) {                                       // no RSTn follows: the host decoder stops decoding here ("ended")
           rc = (my == f.mcuy - 1 && mx == f.mcux - 1) ? JST_OK : JST_BAD_RESTART;   // unfinished planes are the host decoder's business
           my = f.mcuy; break;
         }
-        dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
+        dc0 = dc1 = dc2 = 0;
         todo = f.restart ? (int)f.restart : 0x7fffffff;
       }
     }

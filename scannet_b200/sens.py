@@ -36,7 +36,7 @@ class SensFile:
         return cls(_handle=h)
 
     def close(self):
-        if self._h:
+        if self._h and _L is not None:                    # (module globals are gone when the interpreter is shutting down)
             _L().scn_sens_close(self._h); self._h = C.c_void_p()
 
     __del__ = close
