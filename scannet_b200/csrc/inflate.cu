@@ -29,22 +29,28 @@
 
 namespace {
 
-struct HuffTab {                     // canonical Huffman code, lengths 1..15
+template <int BITS>
+struct HuffTabT {                    // canonical Huffman code, lengths 1..15
   uint16_t count[16];                // codes per length
   uint16_t first[16];                // first code of each length
   uint16_t offs[16];                 // index of that code's symbol in sym[]
   uint16_t sym[288];
-  uint32_t fast[1024];               // 10-bit lookahead (stream bit order) -> packed entry (below); kLongCode = code longer than 10 bits
+  static constexpr int kBits = BITS;
+  uint32_t fast[1 << BITS];          // BITS-bit lookahead (stream bit order) -> packed entry (below); kLongCode = longer code
 };
 // Packed table entry: everything the main loop needs from one shared-memory load.
 //   bits 0-3 code length, 4-7 number of extra bits, 8-9 kind, 10-14 code length + extra bits, 16-31 value (literal byte /
 //   length base / distance base / symbol)
 enum { K_LIT = 0, K_BASE = 1, K_EOB = 2, K_BAD = 3 };
-constexpr int kFastBits = 10;
-constexpr uint32_t kFastSize = 1u << kFastBits;
+// literal/length codes of a noisy depth frame reach 11-12 bits (5.7 % of the symbols were longer than 9): 10-bit lookahead;
+// the 30 distance codes rarely pass 8 bits.  6.8 KB of tables per stream keeps 26 streams per SM resident when the window
+// lives in HBM (a scan of 3840 frames in one wave).
+constexpr int kLitBits = 10, kDistBits = 8;
+using LitTab = HuffTabT<kLitBits>;
+using DistTab = HuffTabT<kDistBits>;
 constexpr uint32_t kLongCode = K_BAD << 8;           // kind "bad" with code length 0: the code is longer than the lookahead
 enum { M_PLAIN = 0, M_LITLEN = 1, M_DIST = 2 };     // what the symbols of a table mean
-struct InflateScratch { HuffTab lit, dist; uint8_t lens[320]; };
+struct InflateScratch { LitTab lit; DistTab dist; uint8_t lens[320]; };
 constexpr uint32_t kWin = 32768;                                   // deflate window = the shared-memory ring of the device decoder
 struct InflateScratchDev { uint8_t ring[kWin]; InflateScratch s; };
 
@@ -143,8 +149,8 @@ SCN_HD uint32_t make_entry(int mode, unsigned sym, unsigned len) {
 
 // canonical code from code lengths + the 9-bit lookahead table (filled by all lanes together); returns false for an
 // over-subscribed set (incomplete sets are allowed, as in zlib for a single distance code)
-template <int LANES>
-SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mode) {
+template <int LANES, class Tab>
+SCN_HD bool huff_build(Tab& h, const uint8_t* lens, int n, int lane, int mode) {
   // counted privately by every lane (a read-modify-write on the shared table would race between lanes); the shared copies
   // below are then written with identical values by all of them
   uint16_t cnt[16];
@@ -159,6 +165,7 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mod
     code = (code + cnt[l - 1]) << 1;
     h.count[l] = cnt[l]; h.first[l] = (uint16_t)code; h.offs[l] = (uint16_t)off; off += cnt[l];
   }
+  constexpr int kFastBits = Tab::kBits; constexpr uint32_t kFastSize = 1u << kFastBits;
   for (int j = lane; j < (int)kFastSize; j += LANES) h.fast[j] = kLongCode;
   lanes_sync<LANES>();
   uint16_t nexti[16], nextc[16];
@@ -178,7 +185,9 @@ SCN_HD bool huff_build(HuffTab& h, const uint8_t* lens, int n, int lane, int mod
 }
 // decode one symbol into a packed entry whose code bits are already consumed (caller guarantees >= 15 bits in the buffer:
 // bi_refill leaves > 32); an invalid code gives kind K_BAD
-SCN_HD uint32_t huff_decode(BitIn& b, const HuffTab& h, int mode) {
+template <class Tab>
+SCN_HD uint32_t huff_decode(BitIn& b, const Tab& h, int mode) {
+  constexpr int kFastBits = Tab::kBits;
   const uint32_t e = h.fast[bi_peek(b, kFastBits)];
   if (e != kLongCode) { bi_drop(b, (int)(e & 15u)); return e; }
   const unsigned r = rev_bits(bi_peek(b, 15), 15);
@@ -216,7 +225,9 @@ struct FastBits {
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
-__device__ __forceinline__ uint32_t long_code(const HuffTab& h, uint32_t win, int mode) {     // codes of 11..15 bits
+template <class Tab>
+__device__ __forceinline__ uint32_t long_code(const Tab& h, uint32_t win, int mode) {     // codes longer than the lookahead
+  constexpr int kFastBits = Tab::kBits;
   const unsigned r = __brev(win & 0x7FFFu) >> 17;
   for (int l = kFastBits + 1; l < 16; ++l) {
     const unsigned c = (r >> (15 - l)) - h.first[l];
@@ -246,7 +257,7 @@ __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScr
   int rc;
   for (;;) {
     uint32_t win = fb.peek();
-    uint32_t e = lds32(s_lit + ((win << 2) & ((kFastSize - 1u) << 2)));
+    uint32_t e = lds32(s_lit + ((win << 2) & (((1u << kLitBits) - 1u) << 2)));
   dispatch:
     if ((e & 0x300u) == 0u) {                                                                    // literal (every lane stores the same byte to the same place)
       if (o >= cap) { rc = INF_OUT_FULL; break; }
@@ -266,7 +277,7 @@ __device__ __forceinline__ int inflate_block_fast(FastBits& fb, const InflateScr
     uint32_t len = (e >> 16) + ((win & ~(0xFFFFFFFFu << ((e >> 10) & 31u))) >> (e & 15u));        // code + extra bits <= 20
     fb.drop((e >> 10) & 31u);
     win = fb.peek();
-    uint32_t d = lds32(s_dist + ((win << 2) & ((kFastSize - 1u) << 2)));
+    uint32_t d = lds32(s_dist + ((win << 2) & (((1u << kDistBits) - 1u) << 2)));
     if ((d & 0x300u) != (K_BASE << 8)) {
       if (d == kLongCode) d = long_code(S.dist, win, M_DIST);
       if ((d & 0x300u) != (K_BASE << 8)) { rc = INF_BAD_CODE; break; }
