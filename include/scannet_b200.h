@@ -329,7 +329,8 @@ typedef struct scn_fuse_report {
   double   integrate_s;            /* integrator: submit + wait for the GPU, all chunks */
   double   depth_pack_s, depth_kernel_s;     /* of depth_decode_s: host packing + upload issue, inflate kernel (CUDA events) */
   double   color_host_s, color_entropy_s, color_convert_s;   /* of color_decode_s: host parse + pack, Huffman+IDCT kernel, colour kernel */
-  double   setup_s;                /* open + parse the file, create the volume, allocate the staging buffers */
+  double   setup_s;                /* open + parse the file, create the volume */
+  double   buffers_s, teardown_s;  /* of fuse_s: allocating the double-buffered frame arrays; joining the decoders and freeing them */
   double   mc_s, ply_s, total_s;   /* marching cubes, PLY write, everything incl. opening the file */
 } scn_fuse_report_t;
 int  scn_fuse_scene(const char* sens_path, const char* out_ply /* NULL: no mesh */, const scn_tsdf_params* params, int device,

@@ -154,6 +154,7 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
     }
     if (use_color && !rc) { d_lut = (int32_t*)scn_device_alloc(px * 4); if (!d_lut || scn_memcpy_h2d(d_lut, lut.data(), px * 4, nullptr)) fail_here(nullptr); }
     if (!rc && (scn_stream_create(&st_d) || scn_stream_create(&st_c))) fail_here(nullptr);
+    rep.buffers_s = now_s() - t0;
     // per chunk: the frames with a valid pose, compacted (a frame without a pose is never decoded: sensorData.h:382)
     struct ChunkPlan { std::vector<uint64_t> frames; std::vector<float> poses; };
     std::mutex m; std::condition_variable cv;
@@ -252,12 +253,14 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
       { std::lock_guard<std::mutex> l(m); consumed = c + 1; }
       cv.notify_all();
     }
+    const double tt0 = now_s();
     { std::lock_guard<std::mutex> l(m); stop = true; }
     cv.notify_all();
     if (th_d.joinable()) th_d.join();
     if (th_c.joinable()) th_c.join();
     for (int b = 0; b < 2; ++b) { scn_device_free(d_depth[b]); scn_device_free(d_rgb[b]); }
     scn_device_free(d_lut); scn_stream_destroy(st_d); scn_stream_destroy(st_c); scn_host_free(h_rgb);
+    rep.teardown_s = now_s() - tt0;
   } else {
     // host decode is the bottleneck of this mode (one frame = ~2 ms inflate + ~1-3 ms JPEG on one core): up to 64 cores,
     // chunks of two frames per worker

@@ -15,7 +15,7 @@ class FuseReport(C.Structure):
                 ("mesh_vertices", C.c_uint64), ("mesh_faces", C.c_uint64), ("device_bytes_in_use", C.c_uint64),
                 ("fuse_s", C.c_double), ("decode_wait_s", C.c_double), ("depth_decode_s", C.c_double), ("color_decode_s", C.c_double),
                 ("integrate_s", C.c_double), ("depth_pack_s", C.c_double), ("depth_kernel_s", C.c_double),
-                ("color_host_s", C.c_double), ("color_entropy_s", C.c_double), ("color_convert_s", C.c_double), ("setup_s", C.c_double),
+                ("color_host_s", C.c_double), ("color_entropy_s", C.c_double), ("color_convert_s", C.c_double), ("setup_s", C.c_double), ("buffers_s", C.c_double), ("teardown_s", C.c_double),
                 ("mc_s", C.c_double), ("ply_s", C.c_double), ("total_s", C.c_double)]
 
     def as_dict(self):
