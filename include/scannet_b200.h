@@ -318,6 +318,7 @@ typedef struct scn_fuse_report {
   int32_t  status;                 /* 0 or the error code of this scene (scn_fuse_many) */
   int32_t  device;
   int32_t  gpu_decode;             /* 1 = payloads were decoded on the GPU */
+  uint32_t volume_reused;          /* scn_fuse_many: the worker's volume of the previous scene was reset instead of a new one created */
   uint32_t color_frames_on_device; /* JPEG frames the device decoder handled itself (the rest went through the host decoder) */
   uint64_t frames_integrated, frames_skipped, frames_skipped_pose;
   uint64_t blocks_allocated, voxels_updated;
@@ -336,6 +337,8 @@ typedef struct scn_fuse_report {
 int  scn_fuse_scene(const char* sens_path, const char* out_ply /* NULL: no mesh */, const scn_tsdf_params* params, int device,
                     const char* decode_mode, scn_fuse_report_t* report);
 /* n_scenes scenes over n_devices GPUs, one scene per GPU at a time, no data-path collective; reports[i] per scene */
+/* sizeof(scn_fuse_report_t) of the library build, for bindings that mirror the struct (tests/test_abi_cpu.py) */
+size_t scn_fuse_report_sizeof(void);
 int  scn_fuse_many(const char* const* sens_paths, const char* const* out_plys /* NULL or per-scene NULL: no mesh */, uint32_t n_scenes,
                    const scn_tsdf_params* params, const int* devices, uint32_t n_devices, const char* decode_mode,
                    scn_fuse_report_t* reports);

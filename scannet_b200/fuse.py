@@ -9,7 +9,7 @@ from ._lib import TsdfParams, check, lib
 
 
 class FuseReport(C.Structure):
-    _fields_ = [("status", C.c_int32), ("device", C.c_int32), ("gpu_decode", C.c_int32), ("color_frames_on_device", C.c_uint32),
+    _fields_ = [("status", C.c_int32), ("device", C.c_int32), ("gpu_decode", C.c_int32), ("volume_reused", C.c_uint32), ("color_frames_on_device", C.c_uint32),
                 ("frames_integrated", C.c_uint64), ("frames_skipped", C.c_uint64), ("frames_skipped_pose", C.c_uint64),
                 ("blocks_allocated", C.c_uint64), ("voxels_updated", C.c_uint64),
                 ("mesh_vertices", C.c_uint64), ("mesh_faces", C.c_uint64), ("device_bytes_in_use", C.c_uint64),

@@ -54,3 +54,11 @@ def test_product_never_imports_oracle():
                 if re.search(r"(import|include|CDLL|dlopen)[^\n]*oracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_fuse_report_binding_matches_the_library_struct():
+    import ctypes as C
+    from scannet_b200 import fuse
+    from scannet_b200._lib import lib
+    lib().scn_fuse_report_sizeof.restype = C.c_size_t
+    assert lib().scn_fuse_report_sizeof() == C.sizeof(fuse.FuseReport)
