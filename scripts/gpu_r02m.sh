@@ -5,7 +5,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 PORT=$((29500 + N))
 if [ "$N" = 1 ]; then LAUNCH="python"; else LAUNCH="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT"; fi
-( time timeout 1200 $LAUNCH bench.py --gpus $N --steps 20 --warmup 5 --no-seg > $OUT/bench_n${N}_$TAG.json 2> $OUT/bench_n${N}_$TAG.err ) 2>&1 | tail -3
+( time timeout 1200 $LAUNCH bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n${N}_$TAG.json 2> $OUT/bench_n${N}_$TAG.err ) 2>&1 | tail -3
 python - <<PY
 import json
 j=json.loads(open('$OUT/bench_n${N}_$TAG.json').read().strip().splitlines()[-1])
