@@ -8,7 +8,10 @@
 //   writer                 :888-929 initDefault/addFrame, :648-691 compressDepth, :1101-1109 saveToFile
 //   saveToImages / PGM     :1342-1466, savePoseFile :1706-1714, operator<< :1941-1955
 // Errors never cross the boundary as exceptions: every entry point returns a status.
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdint>
@@ -339,10 +342,20 @@ void scn::png_encode_stb(const uint8_t* px, uint32_t w, uint32_t h, int n, std::
 }
 
 // ------------------------------------------------------------------------------ container
+// a compressed payload: a view into the mapped file (reader) or owned bytes (writer)
+struct scn_blob {
+  const uint8_t* p = nullptr; size_t n = 0; std::vector<uint8_t> own;
+  const uint8_t* data() const { return own.empty() ? p : own.data(); }
+  size_t size() const { return own.empty() ? n : own.size(); }
+  bool empty() const { return size() == 0; }
+  void view(const uint8_t* q, size_t m) { own.clear(); p = q; n = m; }
+  void assign(const uint8_t* a, const uint8_t* b) { p = nullptr; n = 0; own.assign(a, b); }
+  std::vector<uint8_t>& owned() { p = nullptr; n = 0; return own; }
+};
 struct scn_sens_frame {
   float cam2world[16];
   uint64_t ts_color = 0, ts_depth = 0;
-  std::vector<uint8_t> color, depth;          // compressed payloads as stored in the file
+  scn_blob color, depth;                      // compressed payloads as stored in the file
 };
 struct scn_sens {
   uint32_t version = 4;
@@ -353,11 +366,24 @@ struct scn_sens {
   float depth_shift = 1000.0f;
   std::vector<scn_sens_frame> frames;
   std::vector<std::vector<uint8_t>> imu;      // 128-byte records (sensorData.h:786-833), kept verbatim
+  // the file an opened stream was read from: mapped read-only (the payloads above point into it; a scan is 0.4-3 GB and
+  // copying every payload into its own vector cost as much as fusing the scan) or, where mmap is not possible, read whole
+  const uint8_t* file = nullptr; size_t file_len = 0; bool mapped = false; std::vector<uint8_t> file_buf;
+  ~scn_sens() { if (mapped && file) munmap(const_cast<uint8_t*>(file), file_len); }
 };
 
 namespace {
 void identity16(float* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
-template <typename T> bool rd(std::istream& in, T& v) { in.read((char*)&v, sizeof(T)); return (bool)in; }
+// istream-like cursor over the mapped file: a read past the end fails and every later read fails too
+struct MemIn {
+  const uint8_t* p; uint64_t n, pos = 0; bool ok = true;
+  MemIn(const uint8_t* p_, uint64_t n_) : p(p_), n(n_) {}
+  void read(char* dst, uint64_t k) { if (!ok || k > n - pos) { ok = false; return; } memcpy(dst, p + pos, k); pos += k; }
+  const uint8_t* take(uint64_t k) { if (!ok || k > n - pos) { ok = false; return nullptr; } const uint8_t* q = p + pos; pos += k; return q; }
+  int64_t tellg() const { return ok ? (int64_t)pos : -1; }
+  explicit operator bool() const { return ok; }
+};
+template <typename T> bool rd(MemIn& in, T& v) { in.read((char*)&v, sizeof(T)); return (bool)in; }
 const uint64_t kMaxPayload = 1ull << 31;
 }  // namespace
 
@@ -365,12 +391,26 @@ extern "C" {
 
 int scn_sens_open(const char* path, scn_sens** out) {
   if (!path || !out) return scn::fail(SCN_ERR_ARG, "null argument");
-  std::ifstream in(path, std::ios::binary);
-  if (!in.is_open()) return scn::fail(SCN_ERR_IO, "could not open file %s", path);         // sensorData.h:1253-1255
-  in.seekg(0, std::ios::end); const uint64_t file_size = (uint64_t)std::max<std::streamoff>(in.tellg(), 0); in.seekg(0, std::ios::beg);
-  // every count / size field is checked against what the file can still hold before anything is allocated for it
-  auto left = [&]() { const std::streamoff p = in.tellg(); return p < 0 ? (uint64_t)0 : file_size - std::min<uint64_t>(file_size, (uint64_t)p); };
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) return scn::fail(SCN_ERR_IO, "could not open file %s", path);                 // sensorData.h:1253-1255
+  struct stat stt;
+  if (fstat(fd, &stt) != 0 || S_ISDIR(stt.st_mode)) { ::close(fd); return scn::fail(SCN_ERR_IO, "could not open file %s", path); }
+  const uint64_t file_size = (uint64_t)std::max<off_t>(stt.st_size, 0);
   scn_sens* s = new scn_sens();
+  if (file_size && !getenv("SCN_SENS_NO_MMAP")) {
+    void* m = mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m != MAP_FAILED) { s->file = (const uint8_t*)m; s->file_len = file_size; s->mapped = true; madvise(m, file_size, MADV_WILLNEED); }
+  }
+  if (!s->mapped && file_size) {                                 // no mmap (special file systems): read the file whole
+    s->file_buf.resize(file_size);
+    uint64_t got = 0;
+    while (got < file_size) { const ssize_t r = ::read(fd, s->file_buf.data() + got, file_size - got); if (r <= 0) break; got += (uint64_t)r; }
+    s->file_buf.resize(got); s->file = s->file_buf.data(); s->file_len = got;
+  }
+  ::close(fd);
+  MemIn in(s->file, s->file_len);
+  // every count / size field is checked against what the file can still hold before anything is allocated for it
+  auto left = [&]() { const int64_t p = in.tellg(); return p < 0 ? (uint64_t)0 : file_size - std::min<uint64_t>(file_size, (uint64_t)p); };
   auto bail = [&](int code, const char* msg) { delete s; return scn::fail(code, "%s: %s", path, msg); };
   if (!rd(in, s->version)) return bail(SCN_ERR_FORMAT, "truncated header");
   if (s->version != 4) {                                                                     // :882-886
@@ -396,10 +436,9 @@ int scn_sens_open(const char* path, scn_sens** out) {
     if (!rd(in, f.ts_color) || !rd(in, f.ts_depth) || !rd(in, cb) || !rd(in, db)) return bail(SCN_ERR_FORMAT, "truncated frame header");
     if (cb > kMaxPayload || db > kMaxPayload) return bail(SCN_ERR_FORMAT, "implausible payload size");
     if (cb + db > left()) return bail(SCN_ERR_FORMAT, "truncated frame payload");
-    f.color.resize(cb); f.depth.resize(db);
-    if (cb) in.read((char*)f.color.data(), (std::streamsize)cb);
-    if (db) in.read((char*)f.depth.data(), (std::streamsize)db);
+    const uint8_t* cp = in.take(cb); const uint8_t* dp = in.take(db);        // views into the mapped file
     if (!in) return bail(SCN_ERR_FORMAT, "truncated frame payload");
+    f.color.view(cp, cb); f.depth.view(dp, db);
   }
   uint64_t ni = 0;
   if (rd(in, ni) && ni > 0) {
@@ -552,7 +591,10 @@ int scn_sens_set_pose(scn_sens* s, uint64_t i, const float cam2world[16]) {
 
 int scn_sens_save(const scn_sens* s, const char* path) {
   if (!s || !path) return scn::fail(SCN_ERR_ARG, "null argument");
-  std::ofstream out(path, std::ios::binary);
+  // a stream opened from a file points into its mapping: never truncate that file in place (pose write-back saves over the
+  // input) - write beside it and rename
+  const std::string tmp = s->mapped ? std::string(path) + ".tmp" + std::to_string((long long)getpid()) : std::string(path);
+  std::ofstream out(tmp, std::ios::binary);
   if (!out) return scn::fail(SCN_ERR_IO, "Unable to open file for writing: %s", path);       // sensorData.h:1103-1105
   out.write((const char*)&s->version, 4);
   const uint64_t slen = s->sensor_name.size();
@@ -574,7 +616,10 @@ int scn_sens_save(const scn_sens* s, const char* path) {
   const uint64_t ni = s->imu.size();
   out.write((const char*)&ni, 8);
   for (const auto& r : s->imu) out.write((const char*)r.data(), 128);
-  return out ? SCN_OK : scn::fail(SCN_ERR_IO, "write failed: %s", path);
+  out.close();
+  if (!out) { if (s->mapped) remove(tmp.c_str()); return scn::fail(SCN_ERR_IO, "write failed: %s", path); }
+  if (s->mapped && rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return scn::fail(SCN_ERR_IO, "Unable to open file for writing: %s", path); }
+  return SCN_OK;
 }
 
 int scn_sens_create(uint32_t cw, uint32_t ch, uint32_t dw, uint32_t dh, const float color_intr[16], const float depth_intr[16],
@@ -604,7 +649,7 @@ int scn_sens_add_frame(scn_sens* s, const uint8_t* color, uint64_t color_bytes, 
   if (depth) {
     const size_t raw = (size_t)s->dw * s->dh * 2;
     if (s->depth_comp == 0) f.depth.assign((const uint8_t*)depth, (const uint8_t*)depth + raw);
-    else scn::zlib_deflate((const uint8_t*)depth, raw, f.depth);
+    else scn::zlib_deflate((const uint8_t*)depth, raw, f.depth.owned());
   }
   s->frames.push_back(std::move(f));
   return SCN_OK;

@@ -25,7 +25,7 @@ def main():
             m = re.search(r"Function : (\S+)", ln)
             if m:
                 kern = m.group(1); hist[kern] = collections.Counter(); continue
-            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", ln)
+            m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", ln)
             if m and kern:
                 hist[kern][m.group(1)] += 1
         if not hist:

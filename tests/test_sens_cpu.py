@@ -400,3 +400,31 @@ def test_oversubscribed_jpeg_huffman_table_is_rejected_before_any_table_write(tm
         s = SensFile(p)
         with pytest.raises(ScnError):
             s.color(0)
+
+
+def test_pose_write_back_over_the_opened_file_and_unmapped_open(tmp_path, built, monkeypatch):
+    """An opened stream points into the mapped file: saving over that very file (the pose write-back workflow) must not
+    truncate the mapping, and the read-whole fallback (SCN_SENS_NO_MMAP) gives the same bytes."""
+    D, Cc, P, K = synth.make_frames(4, seed=9, width=96, height=64, loop_frames=30, noise_mm=1.0)
+    w = SensFile.create((96, 64), (96, 64), K, K, color_compression=0, depth_compression=1)
+    for f in range(4):
+        w.add_frame(Cc[f], D[f], P[f], f, f)
+    p = str(tmp_path / "scan.sens"); w.save(p)
+    before = open(p, "rb").read()
+    s = SensFile(p)
+    T = np.eye(4, dtype=np.float32); T[1, 3] = -2.25
+    s.set_pose(2, T)
+    s.save(p)                                             # over the input
+    assert (s.depth(3) == D[3]).all() and (s.color(0) == Cc[0]).all()      # the old mapping is still intact
+    after = open(p, "rb").read()
+    assert len(after) == len(before) and after != before
+    assert not [f for f in os.listdir(tmp_path) if ".tmp" in f]
+    s2 = SensFile(p)
+    assert (s2.pose(2) == T).all() and (s2.pose(1) == P[1]).all() and (s2.depth(0) == D[0]).all()
+    monkeypatch.setenv("SCN_SENS_NO_MMAP", "1")
+    s3 = SensFile(p)
+    assert s3.n_frames == 4 and (s3.pose(2) == T).all()
+    for f in range(4):
+        assert (s3.depth(f) == D[f]).all() and (s3.color(f) == Cc[f]).all()
+    p3 = str(tmp_path / "copy.sens"); s3.save(p3)
+    assert open(p3, "rb").read() == after
