@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "scn_common.h"
+#include "stage_pool.h"
 
 namespace {
 
@@ -108,16 +109,23 @@ struct SceneJob {
 };
 
 // What a worker of scn_fuse_many keeps from one scene to the next on its GPU: the volume (16 GiB of voxel blocks by default:
-// cudaMalloc + first clear cost 0.15-0.4 s, a reset of the used blocks a few ms) and the double-buffered frame arrays.
+// cudaMalloc + first clear cost 0.15-0.4 s, a reset of the used blocks a few ms).
 struct SceneCache {
   scn_tsdf* vol = nullptr; scn_tsdf_params p;
+  void release() { if (vol) scn_tsdf_destroy(vol); vol = nullptr; }
+};
+// The double-buffered frame arrays of the GPU-decode mode (3 GB at 1024-frame chunks with colour) come from a per-device pool
+// like the decoders' staging: allocating and freeing them per scene cost up to 0.2 s (cudaFree synchronises the device).
+struct FrameBufs {
+  int device = 0;
   void* buf[4] = {nullptr, nullptr, nullptr, nullptr}; size_t cap[4] = {0, 0, 0, 0};       // depth x2, colour x2
   void* take(int i, size_t bytes) {
     if (bytes > cap[i]) { scn_device_free(buf[i]); buf[i] = scn_device_alloc(bytes); cap[i] = buf[i] ? bytes : 0; }
     return buf[i];
   }
-  void release() { if (vol) scn_tsdf_destroy(vol); vol = nullptr; for (int i = 0; i < 4; ++i) { scn_device_free(buf[i]); buf[i] = nullptr; cap[i] = 0; } }
+  void release() { for (int i = 0; i < 4; ++i) { scn_device_free(buf[i]); buf[i] = nullptr; cap[i] = 0; } }
 };
+scn::StagePool<FrameBufs>& frame_pool() { static auto* p = new scn::StagePool<FrameBufs>(); return *p; }
 
 int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cache = nullptr) {
   scn_fuse_report_t rep; memset(&rep, 0, sizeof(rep));
@@ -167,9 +175,10 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cach
     const uint64_t n_chunks = (in.n_frames + CH - 1) / CH;
     uint16_t* d_depth[2] = {nullptr, nullptr}; uint8_t* d_rgb[2] = {nullptr, nullptr}; int32_t* d_lut = nullptr;
     void* st_d = nullptr; void* st_c = nullptr;
+    scn::StagePool<FrameBufs>::Lease fb(frame_pool());
     for (int b = 0; b < 2; ++b) {
-      d_depth[b] = (uint16_t*)(cache ? cache->take(b, (size_t)CH * px * 2) : scn_device_alloc((size_t)CH * px * 2));
-      if (use_color) d_rgb[b] = (uint8_t*)(cache ? cache->take(2 + b, (size_t)CH * px * 3) : scn_device_alloc((size_t)CH * px * 3));
+      d_depth[b] = (uint16_t*)fb->take(b, (size_t)CH * px * 2);
+      if (use_color) d_rgb[b] = (uint8_t*)fb->take(2 + b, (size_t)CH * px * 3);
       if (!d_depth[b] || (use_color && !d_rgb[b])) fail_here(nullptr);
     }
     if (use_color && !rc) { d_lut = (int32_t*)scn_device_alloc(px * 4); if (!d_lut || scn_memcpy_h2d(d_lut, lut.data(), px * 4, nullptr)) fail_here(nullptr); }
@@ -278,7 +287,6 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cach
     cv.notify_all();
     if (th_d.joinable()) th_d.join();
     if (th_c.joinable()) th_c.join();
-    if (!cache) for (int b = 0; b < 2; ++b) { scn_device_free(d_depth[b]); scn_device_free(d_rgb[b]); }
     scn_device_free(d_lut); scn_stream_destroy(st_d); scn_stream_destroy(st_c); scn_host_free(h_rgb);
     rep.teardown_s = now_s() - tt0;
   } else {
@@ -340,6 +348,7 @@ std::string default_out(const std::string& sens_path) { return sens_path.substr(
 
 extern "C" {
 
+void scn_fuse_release_staging_() { frame_pool().trim(); }
 size_t scn_fuse_report_sizeof(void) { return sizeof(scn_fuse_report_t); }
 
 int scn_fuse_scene(const char* sens_path, const char* out_ply, const scn_tsdf_params* params, int device, const char* decode_mode, scn_fuse_report_t* report) {

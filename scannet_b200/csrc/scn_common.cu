@@ -88,7 +88,9 @@ int scn_memcpy_d2h(void* dst, const void* d_src, size_t bytes, void* stream) {
 // Creates the CUDA context (≈0.3 s on a cold process) — the CLIs call it on a helper thread while they read their input file.
 extern "C" void scn_inflate_release_staging_();
 extern "C" void scn_jpeg_release_staging_();
-int scn_release_cached_staging(void) { scn_inflate_release_staging_(); scn_jpeg_release_staging_(); return SCN_OK; }
+extern "C" void scn_fuse_release_staging_();
+int scn_current_device_(void) { int d = 0; cudaGetDevice(&d); return d; }
+int scn_release_cached_staging(void) { scn_inflate_release_staging_(); scn_jpeg_release_staging_(); scn_fuse_release_staging_(); return SCN_OK; }
 int scn_cuda_warmup(void) { return cudaFree(0) == cudaSuccess ? SCN_OK : scn::fail(SCN_ERR_CUDA, "no usable CUDA device"); }
 
 }  // extern "C"

@@ -2,11 +2,11 @@
 // (cudaHostAlloc ~0.2 ms per MB) and the scene driver decodes on short-lived threads, so they are pooled per device for the
 // life of the process: a call leases one, the lease returns it.  T needs `int device`, a default constructor and release().
 #pragma once
-#include <cuda_runtime.h>
-
 #include <memory>
 #include <mutex>
 #include <vector>
+
+extern "C" int scn_current_device_(void);      // cudaGetDevice of the calling thread (scn_common.cu); keeps this header free of CUDA includes
 
 namespace scn {
 
@@ -16,7 +16,7 @@ class StagePool {
   class Lease {
    public:
     Lease(StagePool& p) : pool_(p) {
-      int dev = 0; cudaGetDevice(&dev);
+      const int dev = scn_current_device_();
       {
         std::lock_guard<std::mutex> l(p.m_);
         for (size_t i = 0; i < p.idle_.size(); ++i)
@@ -32,7 +32,7 @@ class StagePool {
   };
   // frees every idle stage of the calling thread's current device (scn_release_cached_staging)
   void trim() {
-    int dev = 0; cudaGetDevice(&dev);
+    const int dev = scn_current_device_();
     std::vector<std::unique_ptr<T>> mine;
     {
       std::lock_guard<std::mutex> l(m_);
