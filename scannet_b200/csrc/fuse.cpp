@@ -108,9 +108,11 @@ struct SceneJob {
   const char* decode_mode = nullptr;        // "gpu", "host" or null (automatic)
 };
 
-// What a worker of scn_fuse_many keeps from one scene to the next on its GPU: the volume (16 GiB of voxel blocks by default:
-// cudaMalloc + first clear cost 0.15-0.4 s, a reset of the used blocks a few ms).
-struct SceneCache {
+// The volume (16 GiB of voxel blocks with the CLI's defaults: cudaMalloc + first clear + cudaFree cost 0.15-0.4 s, as much as
+// fusing a 5,578-frame scan; a reset clears only the used blocks in a few ms) is kept per device from one scene to the next - by
+// the workers of scn_fuse_many and by consecutive scn_fuse_scene calls of a process alike; scn_release_cached_staging frees it.
+struct VolSlot {
+  int device = 0;
   scn_tsdf* vol = nullptr; scn_tsdf_params p;
   void release() { if (vol) scn_tsdf_destroy(vol); vol = nullptr; }
 };
@@ -126,8 +128,9 @@ struct FrameBufs {
   void release() { for (int i = 0; i < 4; ++i) { scn_device_free(buf[i]); buf[i] = nullptr; cap[i] = 0; } }
 };
 scn::StagePool<FrameBufs>& frame_pool() { static auto* p = new scn::StagePool<FrameBufs>(); return *p; }
+scn::StagePool<VolSlot>& vol_pool() { static auto* p = new scn::StagePool<VolSlot>(); return *p; }
 
-int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cache = nullptr) {
+int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out) {
   scn_fuse_report_t rep; memset(&rep, 0, sizeof(rep));
   rep.device = job.device;
   const double t_begin = now_s();
@@ -147,14 +150,15 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cach
     printf("fusing %s: %llu frames %ux%u, voxel %.4f m, truncation %.3f+%.3f*d\n", job.sens_path.c_str(), (unsigned long long)in.n_frames, in.depth_width,
            in.depth_height, p.voxel_size, p.trunc_base, p.trunc_scale);
   scn_tsdf* vol = nullptr;
-  if (cache && cache->vol && !memcmp(&cache->p, &p, sizeof(p))) {                      // same volume layout as the previous scene of this worker
-    vol = cache->vol;
-    if (scn_tsdf_reset(vol)) { const std::string e = scn_last_error(); scn_sens_close(s); return scn::fail(SCN_ERR_CUDA, "%s", e.c_str()); }
+  scn::StagePool<VolSlot>::Lease vs(vol_pool());
+  if (vs->vol && !memcmp(&vs->p, &p, sizeof(p))) {                                     // same volume layout as the previous scene on this GPU
+    vol = vs->vol;
+    if (scn_tsdf_reset(vol)) { const std::string e = scn_last_error(); vs->release(); scn_sens_close(s); return scn::fail(SCN_ERR_CUDA, "%s", e.c_str()); }
     rep.volume_reused = 1;
   } else {
-    if (cache && cache->vol) { scn_tsdf_destroy(cache->vol); cache->vol = nullptr; }
+    vs->release();
     if (scn_tsdf_create(&p, job.device, &vol)) { const std::string e = scn_last_error(); scn_sens_close(s); return scn::fail(SCN_ERR_CUDA, "%s", e.c_str()); }
-    if (cache) { cache->vol = vol; cache->p = p; }
+    vs->vol = vol; vs->p = p;
   }
   const size_t px = (size_t)in.depth_width * in.depth_height;
   std::vector<int32_t> lut; if (use_color) build_color_lut(in, lut);
@@ -335,7 +339,7 @@ int fuse_scene(const SceneJob& job, scn_fuse_report_t* rep_out, SceneCache* cach
       scn_free(xyz); scn_free(rgb); scn_free(tri);
     }
   }
-  if (!cache) scn_tsdf_destroy(vol);
+  if (rc) vs->release();                                       // do not hand a volume of unknown state to the next scene
   scn_sens_close(s);
   rep.total_s = now_s() - t_begin;
   if (rep_out) *rep_out = rep;
@@ -348,7 +352,7 @@ std::string default_out(const std::string& sens_path) { return sens_path.substr(
 
 extern "C" {
 
-void scn_fuse_release_staging_() { frame_pool().trim(); }
+void scn_fuse_release_staging_() { frame_pool().trim(); vol_pool().trim(); }
 size_t scn_fuse_report_sizeof(void) { return sizeof(scn_fuse_report_t); }
 
 int scn_fuse_scene(const char* sens_path, const char* out_ply, const scn_tsdf_params* params, int device, const char* decode_mode, scn_fuse_report_t* report) {
@@ -365,14 +369,13 @@ int scn_fuse_many(const char* const* sens_paths, const char* const* out_plys, ui
   std::atomic<uint32_t> next{0}; std::atomic<int> rc{0};
   std::mutex em; std::string first_err;
   auto worker = [&](int dev) {
-    SceneCache cache;
     for (;;) {
       const uint32_t i = next.fetch_add(1);
-      if (i >= n_scenes) { scn_set_device(dev); cache.release(); break; }
+      if (i >= n_scenes) break;
       SceneJob j; j.sens_path = sens_paths[i]; j.out_path = out_plys && out_plys[i] ? out_plys[i] : ""; j.params = *params; j.device = dev; j.verbose = false;
       j.decode_mode = decode_mode;
       scn_fuse_report_t r; memset(&r, 0, sizeof(r));
-      const int e = fuse_scene(j, &r, &cache);
+      const int e = fuse_scene(j, &r);
       r.status = e;
       if (reports) reports[i] = r;
       if (e) { std::lock_guard<std::mutex> l(em); if (!rc.load()) { first_err = scn_last_error(); rc.store(e); } }

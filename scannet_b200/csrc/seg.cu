@@ -14,8 +14,8 @@
 //                 partitioned by ALL CTAs with a parallel formulation of __unguarded_partition
 //                 (the k-th element >= pivot from the left swaps with the k-th element <= pivot from
 //                 the right while their positions have not crossed; two device-wide scans per level);
-//         tier 2  one thread per remaining segment (<= kSmall records) runs the literal sequential
-//                 introsort loop + insertion sort on its own contiguous records.
+//         tier 2  one warp per remaining segment (<= kSmall records): the warp stages the segment in shared memory,
+//                 lane 0 runs the literal sequential introsort loop + insertion sort there.
 //       The final __final_insertion_sort pass never moves a record across a partition boundary, so
 //       running it per segment is identical to running it over the whole array.
 //   S5-S7 Kruskal-with-threshold, small-segment merge and labelling (segmentator.cpp:71-91,236-250)
