@@ -34,8 +34,9 @@ int  scn_version(void);
 int  scn_device_count(void);
 /* Creates the CUDA context now (≈0.3 s in a cold process); safe to call from a helper thread while input files are read. */
 int  scn_cuda_warmup(void);
-/* The batch decoders (scn_inflate_batch_device, scn_jpeg_decode_batch_device, scn_fuse_*) keep their pinned upload slices and
- * device scratch buffers in a per-device pool for the life of the process; this frees the idle ones of the current device. */
+/* The batch decoders (scn_inflate_batch_device, scn_jpeg_decode_batch_device) keep their pinned upload slices and device scratch
+ * buffers, and scn_fuse_* its frame arrays and its last volume, in per-device pools for the life of the process; this frees the
+ * idle ones of the current device. */
 int  scn_release_cached_staging(void);
 /* Pinned host memory for frame staging (cudaHostAlloc); integrate calls detect it and skip the bounce copy. */
 void* scn_host_alloc(size_t bytes);
@@ -318,7 +319,7 @@ typedef struct scn_fuse_report {
   int32_t  status;                 /* 0 or the error code of this scene (scn_fuse_many) */
   int32_t  device;
   int32_t  gpu_decode;             /* 1 = payloads were decoded on the GPU */
-  uint32_t volume_reused;          /* scn_fuse_many: the worker's volume of the previous scene was reset instead of a new one created */
+  uint32_t volume_reused;          /* the pooled volume of the previous scene on this GPU was reset instead of a new one created */
   uint32_t color_frames_on_device; /* JPEG frames the device decoder handled itself (the rest went through the host decoder) */
   uint64_t frames_integrated, frames_skipped, frames_skipped_pose;
   uint64_t blocks_allocated, voxels_updated;
