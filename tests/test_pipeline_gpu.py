@@ -169,3 +169,29 @@ def test_fuse_many_scenes_library_driver(built, tmp_path):
     from scannet_b200 import ScnError
     with pytest.raises(ScnError):
         sfuse.fuse_many(paths + [str(tmp_path / "missing.sens")], None, devices=devs, **over)
+
+
+def test_pooled_volume_is_reset_between_scenes_and_can_be_released(built, tmp_path):
+    """Consecutive scenes of a process reuse the pooled volume (reset, not re-created): the second run of the same scene writes the
+    same mesh bytes; a different scene in between leaves nothing behind; scn_release_cached_staging drops the pool."""
+    from scannet_b200 import fuse as sfuse
+    from scannet_b200._lib import lib
+    paths = []
+    for i in range(2):
+        D, Cc, P, K = synth.make_frames(18 + 6 * i, seed=40 + i, width=160, height=120, loop_frames=400)
+        p = tmp_path / f"s{i}.sens"
+        synth.write_sens(str(p), D, None, P, K, depth_comp=1, color_comp=0)
+        paths.append(str(p))
+    over = dict(voxel_size=0.008, trunc_base=0.04, max_blocks=50000, hash_slots=1 << 18)
+    assert lib().scn_release_cached_staging() == 0
+    a = sfuse.fuse_scene(paths[0], str(tmp_path / "a.ply"), **over)
+    b = sfuse.fuse_scene(paths[1], str(tmp_path / "b.ply"), **over)           # other scene, same layout: reuses a's volume
+    c = sfuse.fuse_scene(paths[0], str(tmp_path / "c.ply"), **over)
+    assert a["volume_reused"] == 0 and b["volume_reused"] == 1 and c["volume_reused"] == 1
+    assert (tmp_path / "a.ply").read_bytes() == (tmp_path / "c.ply").read_bytes()
+    assert a["blocks_allocated"] == c["blocks_allocated"] and a["voxels_updated"] == c["voxels_updated"]
+    d = sfuse.fuse_scene(paths[0], None, **dict(over, max_blocks=40000))          # other layout: a new volume
+    assert d["volume_reused"] == 0 and d["voxels_updated"] == a["voxels_updated"]
+    assert lib().scn_release_cached_staging() == 0
+    e = sfuse.fuse_scene(paths[0], None, **dict(over, max_blocks=40000))
+    assert e["volume_reused"] == 0
