@@ -313,6 +313,23 @@ __device__ __forceinline__ int chroma_at(const unsigned char* P, unsigned w2, un
   return (x & 1) ? (3 * ta + tb + 8) >> 4 : (3 * tb + ta + 8) >> 4;
 }
 #define FIX20(x) (((int)((x) * 4096.0f + 0.5f)) << 8)
+// one colour pixel (x, y) of a decoded frame as r | g << 8 | b << 16 (jpeg.cpp: the per-row conversion; stb_image.h:3091-3118)
+__device__ __forceinline__ unsigned pixel_rgb(const FrameDesc& f, const unsigned char* pl, int x, int y) {
+  const int yy = pl[f.plane_off[0] + (size_t)y * f.w2[0] + x];
+  if (f.ncomp == 1) return (unsigned)yy * 0x010101u;
+  int cc[2];
+#pragma unroll
+  for (int k = 1; k <= 2; ++k) {
+    const int hs = f.hmax / f.ch[k], vs = f.vmax / f.cv[k];
+    cc[k - 1] = chroma_at(pl + f.plane_off[k], f.w2[k], f.cy[k], (f.W + hs - 1) / hs, hs, vs, x, y);
+  }
+  const int yf = (yy << 20) + (1 << 19), cr = cc[1] - 128, cb = cc[0] - 128;
+  int r = yf + cr * FIX20(1.40200f);
+  int g = yf + (cr * -FIX20(0.71414f)) + ((cb * -FIX20(0.34414f)) & 0xffff0000);
+  int b = yf + cb * FIX20(1.77200f);
+  r >>= 20; g >>= 20; b >>= 20;
+  return (unsigned)clamp8(r) | ((unsigned)clamp8(g) << 8) | ((unsigned)clamp8(b) << 16);
+}
 // grid: (ceil(out_px / 256), n frames).  lut == nullptr: out pixel p = colour pixel p (out_px = W*H); else out pixel p shows
 // colour pixel lut[p] (-1 = none -> black), the depth-registered sampling of the fusion path.
 __global__ void __launch_bounds__(256)
@@ -325,22 +342,30 @@ k_jpeg_color(const FrameDesc* __restrict__ fd, const unsigned char* __restrict__
   unsigned char* o = out + ((size_t)blockIdx.y * out_px + p) * 3;
   int q = lut ? lut[p] : (int)p;
   if (q < 0) { o[0] = o[1] = o[2] = 0; return; }
-  const int x = q % f.W, y = q / f.W;
+  const unsigned c = pixel_rgb(f, planes + (size_t)blockIdx.y * plane_stride, q % f.W, q / f.W);
+  o[0] = (unsigned char)c; o[1] = (unsigned char)(c >> 8); o[2] = (unsigned char)(c >> 16);
+}
+// whole frames (no map), out_px a multiple of 4: one thread = 4 consecutive pixels = three 32-bit stores (the per-pixel kernel's
+// three byte stores held it at ~340 GB/s).  grid: (ceil(out_px / 1024), n frames)
+__global__ void __launch_bounds__(256)
+k_jpeg_color4(const FrameDesc* __restrict__ fd, const unsigned char* __restrict__ planes, size_t plane_stride, const int* __restrict__ status,
+              unsigned out_px, unsigned char* __restrict__ out) {
+  const FrameDesc& f = fd[blockIdx.y];
+  if (status[blockIdx.y] != JST_OK) return;
+  const unsigned p0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  if (p0 >= out_px) return;
   const unsigned char* pl = planes + (size_t)blockIdx.y * plane_stride;
-  const int yy = pl[f.plane_off[0] + (size_t)y * f.w2[0] + x];
-  if (f.ncomp == 1) { o[0] = o[1] = o[2] = (unsigned char)yy; return; }
-  int cc[2];
+  int x = (int)(p0 % f.W), y = (int)(p0 / f.W);
+  unsigned c[4];
 #pragma unroll
-  for (int k = 1; k <= 2; ++k) {
-    const int hs = f.hmax / f.ch[k], vs = f.vmax / f.cv[k];
-    cc[k - 1] = chroma_at(pl + f.plane_off[k], f.w2[k], f.cy[k], (f.W + hs - 1) / hs, hs, vs, x, y);
+  for (int i = 0; i < 4; ++i) {
+    c[i] = pixel_rgb(f, pl, x, y);
+    if (++x == (int)f.W) { x = 0; ++y; }
   }
-  const int yf = (yy << 20) + (1 << 19), cr = cc[1] - 128, cb = cc[0] - 128;
-  int r = yf + cr * FIX20(1.40200f);
-  int g = yf + (cr * -FIX20(0.71414f)) + ((cb * -FIX20(0.34414f)) & 0xffff0000);
-  int b = yf + cb * FIX20(1.77200f);
-  r >>= 20; g >>= 20; b >>= 20;
-  o[0] = (unsigned char)clamp8(r); o[1] = (unsigned char)clamp8(g); o[2] = (unsigned char)clamp8(b);
+  unsigned* o = reinterpret_cast<unsigned*>(out + ((size_t)blockIdx.y * out_px + p0) * 3);     // 12-byte chunks of 4-byte aligned frames
+  o[0] = c[0] | (c[1] << 24);
+  o[1] = (c[1] >> 8) | (c[2] << 16);
+  o[2] = (c[2] >> 16) | (c[3] << 8);
 }
 
 // ---- host: marker parsing ------------------------------------------------------------------------------------------------------
@@ -582,7 +607,10 @@ int scn_jpeg_decode_batch_device(const uint8_t* const* src, const uint64_t* src_
     if (changed) e = cudaMemcpyAsync(g.d_status, status.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st);
   }
   if (e == cudaSuccess) {
-    k_jpeg_color<<<dim3((out_px + 255) / 256, n), 256, 0, st>>>(g.d_fd, g.d_planes, plane_stride, g.d_status, d_lut, out_px, (unsigned char*)d_out);
+    if (!d_lut && out_px % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
+      k_jpeg_color4<<<dim3((out_px + 1023) / 1024, n), 256, 0, st>>>(g.d_fd, g.d_planes, plane_stride, g.d_status, out_px, (unsigned char*)d_out);
+    else
+      k_jpeg_color<<<dim3((out_px + 255) / 256, n), 256, 0, st>>>(g.d_fd, g.d_planes, plane_stride, g.d_status, d_lut, out_px, (unsigned char*)d_out);
     cudaEventRecord(g.tk[2], st);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
