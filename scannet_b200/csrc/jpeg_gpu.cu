@@ -320,8 +320,9 @@ __device__ __forceinline__ unsigned pixel_rgb(const FrameDesc& f, const unsigned
   int cc[2];
 #pragma unroll
   for (int k = 1; k <= 2; ++k) {
-    const int hs = f.hmax / f.ch[k], vs = f.vmax / f.cv[k];
-    cc[k - 1] = chroma_at(pl + f.plane_off[k], f.w2[k], f.cy[k], (f.W + hs - 1) / hs, hs, vs, x, y);
+    // sampling factors are 1 or 2 (parse_frame admits nothing else): no integer divisions per pixel
+    const int hs = (f.hmax == 2 && f.ch[k] == 1) ? 2 : 1, vs = (f.vmax == 2 && f.cv[k] == 1) ? 2 : 1;
+    cc[k - 1] = chroma_at(pl + f.plane_off[k], f.w2[k], f.cy[k], (f.W + hs - 1) >> (hs - 1), hs, vs, x, y);
   }
   const int yf = (yy << 20) + (1 << 19), cr = cc[1] - 128, cb = cc[0] - 128;
   int r = yf + cr * FIX20(1.40200f);
