@@ -123,3 +123,19 @@ def test_absurd_element_counts_are_errors_not_exceptions(tmp_path, built):
         px = C.POINTER(C.c_float)(); pt = C.POINTER(C.c_uint32)(); nv = C.c_uint64(); nf = C.c_uint64()
         rc = lib().scn_mesh_load(str(p).encode(), C.byref(px), C.byref(nv), C.byref(pt), C.byref(nf))
         assert rc != 0
+
+
+def test_segs_json_integer_formatting_matches_printf(tmp_path, built):
+    """The writer formats the ids itself (no snprintf): same bytes as "%d" for every sign and width."""
+    import ctypes as C
+    import json
+    from scannet_b200._lib import lib
+    rng = np.random.default_rng(3)
+    ids = np.concatenate([np.array([0, 1, 9, 10, 99, 100, -1, -10, 2**31 - 1, -2**31, 123456789], np.int64),
+                          rng.integers(-2**31, 2**31 - 1, 5000), rng.integers(0, 50000, 5000)]).astype(np.int32)
+    p = str(tmp_path / "x.segs.json")
+    assert lib().scn_write_segs_json(p.encode(), b"scene", C.c_float(0.01), C.c_int32(20), ids.ctypes.data_as(C.c_void_p), C.c_uint64(len(ids))) == 0
+    txt = open(p).read()
+    body = txt[txt.index('"segIndices":[') + len('"segIndices":['):-2]
+    assert body == ",".join("%d" % int(v) for v in ids)
+    assert json.loads(txt)["segIndices"] == [int(v) for v in ids]
