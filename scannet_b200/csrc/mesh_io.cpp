@@ -508,23 +508,59 @@ int scn_segmentator_main(int argc, const char** argv) {
 
 int scn_mesh_save_ply(const char* path, const float* xyz, const uint8_t* rgb, uint64_t n_verts, const uint32_t* tri, uint64_t n_faces) {
   if (!path || (!xyz && n_verts) || (!tri && n_faces)) return scn::fail(SCN_ERR_ARG, "null argument");
-  FILE* f = fopen(path, "wb");
-  if (!f) return scn::fail(SCN_ERR_IO, "cannot write %s", path);
-  fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment VCGLIB generated\nelement vertex %llu\nproperty float x\nproperty float y\nproperty float z\n"
+  char head[512];
+  const int hl = snprintf(head, sizeof(head),
+             "ply\nformat binary_little_endian 1.0\ncomment VCGLIB generated\nelement vertex %llu\nproperty float x\nproperty float y\nproperty float z\n"
              "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\nelement face %llu\nproperty list uchar int vertex_indices\nend_header\n",
           (unsigned long long)n_verts, (unsigned long long)n_faces);
-  std::vector<uint8_t> buf;
-  buf.resize((size_t)n_verts * 16);
-  for (uint64_t i = 0; i < n_verts; ++i) {
-    memcpy(&buf[i * 16], xyz + 3 * i, 12);
-    if (rgb) { buf[i * 16 + 12] = rgb[3 * i]; buf[i * 16 + 13] = rgb[3 * i + 1]; buf[i * 16 + 14] = rgb[3 * i + 2]; } else buf[i * 16 + 12] = buf[i * 16 + 13] = buf[i * 16 + 14] = 255;
-    buf[i * 16 + 15] = 255;
+  const size_t vbytes = (size_t)n_verts * 16, fbytes = (size_t)n_faces * 13, total = (size_t)hl + vbytes + fbytes;
+  // records are written by a few threads straight into the mapped output file (a 5.7 M-vertex mesh is 240 MB: building it in a
+  // buffer and fwrite-ing it was one thread at 1.3 GB/s); a plain buffered write is the fallback where the file cannot be mapped
+  auto fill = [&](uint8_t* base, size_t lo, size_t hi) {            // bytes [lo, hi) of the body, on record boundaries
+    for (size_t i = lo / 16; i < std::min<size_t>(n_verts, (hi + 15) / 16) && lo < vbytes; ++i) {
+      uint8_t* r = base + i * 16;
+      memcpy(r, xyz + 3 * i, 12);
+      if (rgb) { r[12] = rgb[3 * i]; r[13] = rgb[3 * i + 1]; r[14] = rgb[3 * i + 2]; } else r[12] = r[13] = r[14] = 255;
+      r[15] = 255;
+    }
+    (void)hi;
+  };
+  const int fd = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) return scn::fail(SCN_ERR_IO, "cannot write %s", path);
+  bool ok = false;
+  if (total > (size_t)(1 << 20) && ftruncate(fd, (off_t)total) == 0) {
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m != MAP_FAILED) {
+      uint8_t* base = (uint8_t*)m;
+      memcpy(base, head, (size_t)hl);
+      uint8_t* vb = base + hl; uint8_t* fb = vb + vbytes;
+      const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      auto work = [&](unsigned t) {
+        const size_t v0 = (size_t)n_verts * t / nt, v1 = (size_t)n_verts * (t + 1) / nt;
+        fill(vb, v0 * 16, v1 * 16);
+        const size_t f0 = (size_t)n_faces * t / nt, f1 = (size_t)n_faces * (t + 1) / nt;
+        for (size_t i = f0; i < f1; ++i) { fb[i * 13] = 3; memcpy(fb + i * 13 + 1, tri + 3 * i, 12); }
+      };
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+      work(0);
+      for (auto& x : th) x.join();
+      ok = munmap(m, total) == 0;
+      ::close(fd);
+      return ok ? SCN_OK : scn::fail(SCN_ERR_IO, "short write on %s", path);
+    }
+    if (ftruncate(fd, 0) != 0) { ::close(fd); return scn::fail(SCN_ERR_IO, "cannot write %s", path); }
   }
-  bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-  buf.resize((size_t)n_faces * 13);
+  FILE* f = fdopen(fd, "wb");
+  if (!f) { ::close(fd); return scn::fail(SCN_ERR_IO, "cannot write %s", path); }
+  ok = fwrite(head, 1, (size_t)hl, f) == (size_t)hl;
+  std::vector<uint8_t> buf(vbytes);
+  fill(buf.data(), 0, vbytes);
+  ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  buf.resize(fbytes);
   for (uint64_t i = 0; i < n_faces; ++i) { buf[i * 13] = 3; memcpy(&buf[i * 13 + 1], tri + 3 * i, 12); }
   ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-  fclose(f);
+  ok = (fclose(f) == 0) && ok;
   return ok ? SCN_OK : scn::fail(SCN_ERR_IO, "short write on %s", path);
 }
 

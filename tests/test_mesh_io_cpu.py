@@ -139,3 +139,30 @@ def test_segs_json_integer_formatting_matches_printf(tmp_path, built):
     body = txt[txt.index('"segIndices":[') + len('"segIndices":['):-2]
     assert body == ",".join("%d" % int(v) for v in ids)
     assert json.loads(txt)["segIndices"] == [int(v) for v in ids]
+
+
+@pytest.mark.parametrize("nv,with_rgb", [(50, True), (50, False), (120000, True), (120000, False)])
+def test_ply_writer_bytes_small_and_mapped_paths(tmp_path, built, nv, with_rgb):
+    """scn_mesh_save_ply: the buffered path (small files) and the mapped multi-threaded path (> 1 MB) write the same VCGLIB-layout
+    bytes: header, 16-byte vertices (xyz + rgba, alpha 255, white without colour), 13-byte triangle records."""
+    import ctypes as C
+    from scannet_b200._lib import lib
+    rng = np.random.default_rng(nv)
+    xyz = rng.standard_normal((nv, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, (nv, 3)).astype(np.uint8)
+    tri = rng.integers(0, nv, (2 * nv, 3)).astype(np.uint32)
+    p = str(tmp_path / "m.ply")
+    rc = lib().scn_mesh_save_ply(p.encode(), xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p) if with_rgb else None, C.c_uint64(nv),
+                                 tri.ctypes.data_as(C.c_void_p), C.c_uint64(len(tri)))
+    assert rc == 0
+    head = ("ply\nformat binary_little_endian 1.0\ncomment VCGLIB generated\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+            "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+            % (nv, len(tri))).encode()
+    v = np.zeros((nv, 16), np.uint8)
+    v[:, :12] = xyz.view(np.uint8).reshape(nv, 12)
+    v[:, 12:15] = rgb if with_rgb else 255
+    v[:, 15] = 255
+    f = np.zeros((len(tri), 13), np.uint8)
+    f[:, 0] = 3
+    f[:, 1:] = tri.view(np.uint8).reshape(len(tri), 12)
+    assert open(p, "rb").read() == head + v.tobytes() + f.tobytes()
